@@ -1,0 +1,60 @@
+// Shared device-side types and helpers.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#define LD_D 256      // latent / model width
+#define LD_H 4        // heads
+#define LD_HD 64      // head dim
+#define LD_EPS 1e-5f  // LayerNorm eps (torch default; nn.LayerNorm at cross_attention.py:277, mdiff_transformer.py:145)
+
+// An activation tensor [rows, ld]: fp32 master and/or bf16 operand planes for the tensor-core GEMMs.
+// Planes are stacked: hi plane rows [0, rows_alloc), lo plane rows [rows_alloc, 2*rows_alloc); value ~= hi + lo.
+struct Act {
+  float* f32;           // may be null
+  __nv_bfloat16* pl;    // may be null
+  int ld;
+  int rows_alloc;       // multiple of 128 so a 128-row TMA box never straddles the planes
+};
+
+enum Epi : int {
+  EPI_BIAS = 0,
+  EPI_RELU = 1,
+  EPI_GELU = 2,      // exact erf GELU (F.gelu default; cross_attention.py:477-478, mdiff_transformer.py:255)
+  EPI_RES = 3,       // res + acc + bias
+  EPI_LN = 4,        // LayerNorm((res?) + acc + bias) * g + b  [+ addv[add_idx[row]]]   (N == 256)
+  EPI_LN_MOD_SILU = 5,  // SiLU(LayerNorm(acc + bias) * (1 + scale) + shift)              (N == 256) StylizationBlock :161-162
+  EPI_SILU = 6
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// hi/lo bf16 split of an fp32 value (lo = bf16(v - float(hi))): v ~= hi + lo to ~16 mantissa bits.
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// nplanes: 0 none, 1 hi only, 2 hi + lo
+__device__ __forceinline__ void act_store(const Act& a, int nplanes, long row, int col, float v) {
+  if (a.f32) a.f32[row * a.ld + col] = v;
+  if (a.pl && nplanes > 0) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    a.pl[row * a.ld + col] = hi;
+    if (nplanes > 1) a.pl[(static_cast<long>(a.rows_alloc) + row) * a.ld + col] = lo;
+  }
+}

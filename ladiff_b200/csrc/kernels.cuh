@@ -1,0 +1,548 @@
+// Non-GEMM kernels of the sampling path: row bookkeeping, embeddings, LayerNorm, the two tiny-key attentions,
+// the ragged (varlen) decoder self-attention, the fused final-LN + CFG + DDIM step, weight packing, feats2joints.
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// row bookkeeping: cnt[S] (rows per sequence) -> off[S+1] (exclusive prefix), total, row -> (seq, t) maps
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ cnt, int S, int* __restrict__ off,
+                                                      int* __restrict__ total) {
+  __shared__ int part[1024];
+  const int chunk = (S + 1023) / 1024;
+  const int b = threadIdx.x * chunk, e = min(S, b + chunk);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += cnt[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      const int t = part[i];
+      part[i] = run;
+      run += t;
+    }
+    off[S] = run;
+    *total = run;
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int i = b; i < e; ++i) {
+    off[i] = run;
+    run += cnt[i];
+  }
+}
+
+// one warp per sequence; dst_stride > 0 additionally writes row_dst[row] = seq * dst_stride + t (decoder scatter map)
+__global__ void k_fill_rows(const int* __restrict__ off, int S, int* __restrict__ row_seq, int* __restrict__ row_t,
+                            int* __restrict__ row_dst, int dst_stride) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= S) return;
+  const int r0 = off[s], n = off[s + 1] - r0;
+  for (int t = lane; t < n; t += 32) {
+    row_seq[r0 + t] = s;
+    row_t[r0 + t] = t;
+    if (row_dst) row_dst[r0 + t] = s * dst_stride + t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic fp32 -> Act conversions
+enum Unary : int { U_COPY = 0, U_RELU = 1, U_SILU = 2 };
+
+__global__ void k_unary(const float* __restrict__ in, int ld_in, int rows, int cols, int op, Act out, int planes) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(rows) * cols) return;
+  const int r = i / cols, c = i % cols;
+  float v = in[static_cast<long>(r) * ld_in + c];
+  if (op == U_RELU) v = fmaxf(v, 0.f);
+  else if (op == U_SILU) v = silu(v);
+  act_store(out, planes, r, c, v);
+}
+
+// LayerNorm over 256 columns, one warp per row.  rows = min(rows_max, *rows_dev).
+__global__ void k_layernorm256(const float* __restrict__ in, int ld_in, int rows_max, const int* __restrict__ rows_dev,
+                               const float* __restrict__ g, const float* __restrict__ b, Act out, int planes) {
+  const int rows = rows_dev ? min(rows_max, *rows_dev) : rows_max;
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[8], s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = in[row * ld_in + lane + 32 * j];
+    s += v[j];
+  }
+  const float mean = warp_sum(s) * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float d = v[j] - mean;
+    q += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.f / 256.f) + LD_EPS);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane + 32 * j;
+    act_store(out, planes, row, c, (v[j] - mean) * rstd * g[c] + b[c]);
+  }
+}
+
+// Sinusoidal timestep embedding, flip_sin_to_cos=True, freq_shift=0, dim 768 -> [cos | sin]
+// (architectures/tools/embeddings.py:245-285).  Frequencies are formed in double and rounded to fp32 so the
+// fp32 product t*f matches torch's to the last bit in almost every entry.
+__global__ void k_sinus_embed(const int* __restrict__ timesteps, int n, Act out, int planes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 768) return;
+  const int r = i / 768, c = i % 768;
+  const int j = c % 384;
+  const float f = static_cast<float>(exp(-9.210340371976184 * static_cast<double>(static_cast<float>(j)) / 384.0));
+  // torch: exponent = (-log(10000) * arange(fp32)) / 384 in fp32, then exp in fp32
+  const float ex = (static_cast<float>(-9.210340371976184) * static_cast<float>(j)) / 384.0f;
+  const float f32 = static_cast<float>(exp(static_cast<double>(ex)));
+  (void)f;
+  const float arg = static_cast<float>(timesteps[r]) * f32;
+  const float v = (c < 384) ? static_cast<float>(cos(static_cast<double>(arg))) : static_cast<float>(sin(static_cast<double>(arg)));
+  act_store(out, planes, r, c, v);
+}
+
+// ca_block hoist: a[(n, s), :] = SiLU(lny[s, :] * (1 + scale[n, :]) + shift[n, :]),  mod row n = [scale(256) | shift(256)]
+// (architectures/mdiff_transformer.py:158-162 with h = LN(y) hoisted out of the step loop).
+__global__ void k_ca_prologue(const float* __restrict__ lny, int ld_lny, const float* __restrict__ mod, int ld_mod,
+                              int n_steps, int S, Act out, int planes) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(n_steps) * S * 256) return;
+  const int c = i & 255;
+  const long rs = i >> 8;
+  const int s = rs % S, n = rs / S;
+  const float v = lny[static_cast<long>(s) * ld_lny + c] * (1.f + mod[static_cast<long>(n) * ld_mod + c]) +
+                  mod[static_cast<long>(n) * ld_mod + 256 + c];
+  act_store(out, planes, rs, c, silu(v));
+}
+
+// x[row, :] = src[(seq % src_mod) * T + t, :] + pe[t, :]   (query_pos: architectures/ladiff_denoiser.py:251)
+__global__ void k_pack_x(const float* __restrict__ src, int src_mod, int T, const float* __restrict__ pe,
+                         const int* __restrict__ row_seq, const int* __restrict__ row_t, const int* __restrict__ R_dev,
+                         Act x, int planes) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long row = i >> 8;
+  const int c = i & 255;
+  if (row >= *R_dev) return;
+  const int s = row_seq[row], t = row_t[row];
+  act_store(x, planes, row, c, src[(static_cast<long>(s % src_mod) * T + t) * 256 + c] + pe[t * 256 + c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// denoiser self-attention (sa_block, architectures/mdiff_transformer.py:307-313): per (sequence, head) the m valid
+// latent rows attend to [m latent rows ; text token ; time token].  One warp per (seq, head); lane owns 2 of 64 dims.
+// The conditioning tokens only act as keys/values (their own outputs are discarded at :313).
+template <int MAXT>
+__global__ void k_attn_small(const float* __restrict__ qkv, const int* __restrict__ off, int S,
+                             const float* __restrict__ textkv, int ld_textkv, const float* __restrict__ timekv,
+                             Act out, int planes) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int s = gw >> 2, h = gw & 3;
+  if (s >= S) return;
+  const int r0 = off[s], m = min(off[s + 1] - r0, MAXT);
+  const int d = h * 64 + 2 * lane;
+  float2 k[MAXT + 2], v[MAXT + 2];
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    if (j < m) {
+      k[j] = *reinterpret_cast<const float2*>(qkv + static_cast<long>(r0 + j) * 768 + 256 + d);
+      v[j] = *reinterpret_cast<const float2*>(qkv + static_cast<long>(r0 + j) * 768 + 512 + d);
+    } else {
+      k[j] = make_float2(0.f, 0.f);
+      v[j] = make_float2(0.f, 0.f);
+    }
+  }
+  k[MAXT] = *reinterpret_cast<const float2*>(textkv + static_cast<long>(s) * ld_textkv + d);
+  v[MAXT] = *reinterpret_cast<const float2*>(textkv + static_cast<long>(s) * ld_textkv + 256 + d);
+  k[MAXT + 1] = *reinterpret_cast<const float2*>(timekv + d);
+  v[MAXT + 1] = *reinterpret_cast<const float2*>(timekv + 256 + d);
+  for (int i = 0; i < m; ++i) {
+    float2 q = *reinterpret_cast<const float2*>(qkv + static_cast<long>(r0 + i) * 768 + d);
+    q.x *= 0.125f;  // 1/sqrt(64), applied to q before q.k^T like nn.MultiheadAttention
+    q.y *= 0.125f;
+    float sc[MAXT + 2], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXT + 2; ++j) {
+      sc[j] = warp_sum(q.x * k[j].x + q.y * k[j].y);
+      if (j >= m && j < MAXT) sc[j] = -INFINITY;  // masked latent slots (key_padding_mask)
+      mx = fmaxf(mx, sc[j]);
+    }
+    float den = 0.f, ox = 0.f, oy = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXT + 2; ++j) {
+      const float p = expf(sc[j] - mx);
+      den += p;
+      ox += p * v[j].x;
+      oy += p * v[j].y;
+    }
+    const float inv = 1.0f / den;
+    act_store(out, planes, r0 + i, d, ox * inv);
+    act_store(out, planes, r0 + i, d + 1, oy * inv);
+  }
+}
+
+// Final LayerNorm (encoder.norm) + CFG combine + DDIM step + next-step input, one warp per (prompt, latent row):
+//   eps = LN(tok_u) + g (LN(tok_c) - LN(tok_u));  lat' = c1 lat + c2 eps   (models/modeltype/ladiff.py:487-492)
+//   x_next[row_u] = x_next[row_c] = lat' + pe[t]                           (ladiff.py:472-474 + ladiff_denoiser.py:251)
+__global__ void k_cfg_ddim(const float* __restrict__ tok, const int* __restrict__ off, int B, int T,
+                           const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ coef,
+                           float guidance, float* __restrict__ lat, const float* __restrict__ pe, Act x, int planes) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int bi = gw / T, t = gw % T;
+  if (bi >= B) return;
+  const int m = off[bi + 1] - off[bi];
+  if (t >= m) return;
+  const long ru = off[bi] + t, rc = off[bi + B] + t;
+  float u[8], c[8], su = 0.f, sc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    u[j] = tok[ru * 256 + lane + 32 * j];
+    c[j] = tok[rc * 256 + lane + 32 * j];
+    su += u[j];
+    sc += c[j];
+  }
+  const float mu = warp_sum(su) * (1.f / 256.f), mc = warp_sum(sc) * (1.f / 256.f);
+  float qu = 0.f, qc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    qu += (u[j] - mu) * (u[j] - mu);
+    qc += (c[j] - mc) * (c[j] - mc);
+  }
+  const float ru_ = 1.0f / sqrtf(warp_sum(qu) * (1.f / 256.f) + LD_EPS);
+  const float rc_ = 1.0f / sqrtf(warp_sum(qc) * (1.f / 256.f) + LD_EPS);
+  const float c1 = coef[0], c2 = coef[1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = lane + 32 * j;
+    const float eu = (u[j] - mu) * ru_ * g[col] + b[col];
+    const float ec = (c[j] - mc) * rc_ * g[col] + b[col];
+    const float eps = eu + guidance * (ec - eu);
+    const long li = (static_cast<long>(bi) * T + t) * 256 + col;
+    const float nl = c1 * lat[li] + c2 * eps;
+    lat[li] = nl;
+    const float xn = nl + pe[t * 256 + col];
+    act_store(x, planes, ru, col, xn);
+    act_store(x, planes, rc, col, xn);
+  }
+}
+
+// standalone CFG + DDIM on dense [B,T,256] tensors (ladiff_cfg_ddim_step)
+__global__ void k_cfg_ddim_dense(const float* __restrict__ pred, float* __restrict__ lat, long n_half, float guidance,
+                                 float c1, float c2) {
+  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n_half) return;
+  const float4 u = *reinterpret_cast<const float4*>(pred + i);
+  const float4 c = *reinterpret_cast<const float4*>(pred + n_half + i);
+  float4 l = *reinterpret_cast<float4*>(lat + i);
+  l.x = c1 * l.x + c2 * (u.x + guidance * (c.x - u.x));
+  l.y = c1 * l.y + c2 * (u.y + guidance * (c.y - u.y));
+  l.z = c1 * l.z + c2 * (u.z + guidance * (c.z - u.z));
+  l.w = c1 * l.w + c2 * (u.w + guidance * (c.w - u.w));
+  *reinterpret_cast<float4*>(lat + i) = l;
+}
+
+// out[s, t, :] = t < m[s] ? LN(tok[row]) : 0      (standalone denoiser_forward: encoder.norm + un-pack)
+__global__ void k_final_ln_out(const float* __restrict__ tok, const int* __restrict__ off, int S, int T,
+                               const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ out) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int s = gw / T, t = gw % T;
+  if (s >= S) return;
+  float* o = out + (static_cast<long>(s) * T + t) * 256;
+  const int m = off[s + 1] - off[s];
+  if (t >= m) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[lane + 32 * j] = 0.f;
+    return;
+  }
+  const long row = off[s] + t;
+  float v[8], sm = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = tok[row * 256 + lane + 32 * j];
+    sm += v[j];
+  }
+  const float mean = warp_sum(sm) * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.f / 256.f) + LD_EPS);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = lane + 32 * j;
+    o[col] = (v[j] - mean) * rstd * g[col] + b[col];
+  }
+}
+
+// z[t, b, :] = t < m[b] ? lat[b, t, :] : 0      (ladiff.py:500 permute + :562-566 re-zeroing)
+__global__ void k_z_out(const float* __restrict__ lat, const int* __restrict__ off, int B, int T, float* __restrict__ z) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(B) * T * 256) return;
+  const int c = i & 255;
+  const long bt = i >> 8;
+  const int t = bt % T, b = bt / T;
+  const int m = off[b + 1] - off[b];
+  z[(static_cast<long>(t) * B + b) * 256 + c] = (t < m) ? lat[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder
+// queries = 0 + pe[:L]  (architectures/ladiff_vae.py:299,334)
+__global__ void k_dec_init(const float* __restrict__ pe, const int* __restrict__ row_t, const int* __restrict__ R_dev,
+                           Act x, int planes) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long row = i >> 8;
+  const int c = i & 255;
+  if (row >= *R_dev) return;
+  act_store(x, planes, row, c, pe[row_t[row] * 256 + c]);
+}
+
+// zrows[moff[b] + t, :] = z[t, b, :] for t < m[b]  (valid memory rows only)
+__global__ void k_gather_z(const float* __restrict__ z, const int* __restrict__ moff, int B, int T, Act out, int planes) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(B) * T * 256) return;
+  const int c = i & 255;
+  const long bt = i >> 8;
+  const int t = bt % T, b = bt / T;
+  const int m = moff[b + 1] - moff[b];
+  if (t < m) act_store(out, planes, moff[b] + t, c, z[(static_cast<long>(t) * B + b) * 256 + c]);
+}
+
+// cross-attention to the <= MAXT valid latent rows of the sequence (operator/cross_attention.py:373-376):
+// one warp per frame row; lane owns 8 dims, 8 lanes per head.
+template <int MAXT>
+__global__ void k_attn_cross(const float* __restrict__ q, const float* __restrict__ memkv, int ld_memkv, int kv_off,
+                             const int* __restrict__ row_seq, const int* __restrict__ moff,
+                             const int* __restrict__ R_dev, Act out, int planes) {
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= *R_dev) return;
+  const int b = row_seq[row];
+  const int m0 = moff[b], m = min(moff[b + 1] - m0, MAXT);
+  const int d = lane * 8;
+  float qv[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(q + row * 256 + d);
+    const float4 c = *reinterpret_cast<const float4*>(q + row * 256 + d + 4);
+    qv[0] = a.x * 0.125f; qv[1] = a.y * 0.125f; qv[2] = a.z * 0.125f; qv[3] = a.w * 0.125f;
+    qv[4] = c.x * 0.125f; qv[5] = c.y * 0.125f; qv[6] = c.z * 0.125f; qv[7] = c.w * 0.125f;
+  }
+  float sc[MAXT], mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    float p = 0.f;
+    if (j < m) {
+      const float* kp = memkv + static_cast<long>(m0 + j) * ld_memkv + kv_off + d;
+      const float4 a = *reinterpret_cast<const float4*>(kp);
+      const float4 c = *reinterpret_cast<const float4*>(kp + 4);
+      p = qv[0] * a.x + qv[1] * a.y + qv[2] * a.z + qv[3] * a.w + qv[4] * c.x + qv[5] * c.y + qv[6] * c.z + qv[7] * c.w;
+    }
+    p += __shfl_xor_sync(0xffffffffu, p, 1);
+    p += __shfl_xor_sync(0xffffffffu, p, 2);
+    p += __shfl_xor_sync(0xffffffffu, p, 4);
+    sc[j] = (j < m) ? p : -INFINITY;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float den = 0.f, o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    if (j < m) {
+      const float p = expf(sc[j] - mx);
+      den += p;
+      const float* vp = memkv + static_cast<long>(m0 + j) * ld_memkv + kv_off + 256 + d;
+      const float4 a = *reinterpret_cast<const float4*>(vp);
+      const float4 c = *reinterpret_cast<const float4*>(vp + 4);
+      o[0] += p * a.x; o[1] += p * a.y; o[2] += p * a.z; o[3] += p * a.w;
+      o[4] += p * c.x; o[5] += p * c.y; o[6] += p * c.z; o[7] += p * c.w;
+    }
+  }
+  const float inv = 1.0f / den;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) act_store(out, planes, row, d + j, o[j] * inv);
+}
+
+// Ragged self-attention over the L valid frames of one sequence (operator/cross_attention.py:367-369), fp32.
+// CTA = (query block of 64, head, sequence), 8 warps x 8 queries (4 at a time).  K^T and V of the (sequence, head)
+// are staged in shared memory once per CTA; nothing is computed or stored for padded frames.
+#define SA_MAXL 256
+#define SA_QB 64
+struct SelfAttnSmem {
+  float Kt[64][SA_MAXL + 1];
+  float Vs[SA_MAXL][64];
+  float Ps[8][SA_MAXL][4];
+  float Qs[8][4][64];
+};
+
+__global__ void __launch_bounds__(256) k_attn_self(const float* __restrict__ qkv, const int* __restrict__ foff, Act out,
+                                                   int planes) {
+  extern __shared__ uint8_t sa_raw[];
+  SelfAttnSmem& sm = *reinterpret_cast<SelfAttnSmem*>(sa_raw);
+  const int b = blockIdx.z, h = blockIdx.y, qb = blockIdx.x;
+  const int r0 = foff[b], L = min(foff[b + 1] - r0, SA_MAXL);
+  if (qb * SA_QB >= L) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < L * 64; i += 256) {
+    const int key = i >> 6, d = i & 63;
+    const float* base = qkv + static_cast<long>(r0 + key) * 768 + h * 64 + d;
+    sm.Kt[d][key] = base[256];
+    sm.Vs[key][d] = base[512];
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    const int q0 = qb * SA_QB + warp * 8 + pass * 4;  // 4 queries q0..q0+3 (warp-uniform)
+    if (q0 >= L) break;
+    for (int i = lane; i < 4 * 64; i += 32) {
+      const int qi = i >> 6, d = i & 63;
+      const int qr = q0 + qi;
+      sm.Qs[warp][qi][d] = (qr < L) ? qkv[static_cast<long>(r0 + qr) * 768 + h * 64 + d] * 0.125f : 0.f;
+    }
+    __syncwarp();
+    float sc[4][SA_MAXL / 32];
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi)
+#pragma unroll
+      for (int i = 0; i < SA_MAXL / 32; ++i) sc[qi][i] = 0.f;
+    for (int d = 0; d < 64; ++d) {
+      float qv[4];
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi) qv[qi] = sm.Qs[warp][qi][d];
+#pragma unroll
+      for (int i = 0; i < SA_MAXL / 32; ++i) {
+        const int key = lane + 32 * i;
+        if (key < L) {
+          const float kv = sm.Kt[d][key];
+#pragma unroll
+          for (int qi = 0; qi < 4; ++qi) sc[qi][i] = fmaf(qv[qi], kv, sc[qi][i]);
+        }
+      }
+    }
+    float inv[4];
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < SA_MAXL / 32; ++i)
+        if (lane + 32 * i < L) mx = fmaxf(mx, sc[qi][i]);
+      mx = warp_max(mx);
+      float den = 0.f;
+#pragma unroll
+      for (int i = 0; i < SA_MAXL / 32; ++i) {
+        const int key = lane + 32 * i;
+        if (key < L) {
+          const float p = expf(sc[qi][i] - mx);
+          den += p;
+          sm.Ps[warp][key][qi] = p;
+        }
+      }
+      inv[qi] = 1.0f / warp_sum(den);
+    }
+    __syncwarp();
+    float o[4][2];
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) o[qi][0] = o[qi][1] = 0.f;
+    for (int key = 0; key < L; ++key) {
+      const float4 p = *reinterpret_cast<const float4*>(&sm.Ps[warp][key][0]);
+      const float v0 = sm.Vs[key][lane], v1 = sm.Vs[key][lane + 32];
+      o[0][0] = fmaf(p.x, v0, o[0][0]); o[0][1] = fmaf(p.x, v1, o[0][1]);
+      o[1][0] = fmaf(p.y, v0, o[1][0]); o[1][1] = fmaf(p.y, v1, o[1][1]);
+      o[2][0] = fmaf(p.z, v0, o[2][0]); o[2][1] = fmaf(p.z, v1, o[2][1]);
+      o[3][0] = fmaf(p.w, v0, o[3][0]); o[3][1] = fmaf(p.w, v1, o[3][1]);
+    }
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      const int qr = q0 + qi;
+      if (qr < L) {
+        act_store(out, planes, r0 + qr, h * 64 + lane, o[qi][0] * inv[qi]);
+        act_store(out, planes, r0 + qr, h * 64 + lane + 32, o[qi][1] * inv[qi]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: W [N, K] (row stride ldw) fp32 -> Wt [K][N] fp32 and bf16 planes [2][n_pad][K] (zero padded rows)
+__global__ void k_pack_weight(const float* __restrict__ W, int ldw, int N, int K, int n_pad, float* __restrict__ Wt,
+                              __nv_bfloat16* __restrict__ pl) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(n_pad) * K) return;
+  const int n = i / K, k = i % K;
+  float v = 0.f;
+  if (n < N) {
+    v = W[static_cast<long>(n) * ldw + k];
+    Wt[static_cast<long>(k) * N + n] = v;
+  }
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  pl[i] = hi;
+  pl[static_cast<long>(n_pad) * K + i] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// feats2joints: de-normalise + recover_from_ric (data/HumanML3D.py:44-48;
+// data/humanml/scripts/motion_process.py:355-381,415-430; quaternion.py:16-20,54-73).  One CTA per sequence:
+// the two cumulative sums over frames (root yaw, root XZ) are block scans, then every (frame, joint) is independent.
+__global__ void __launch_bounds__(256) k_feats2joints(const float* __restrict__ feats, const float* __restrict__ mean,
+                                                      const float* __restrict__ stdv, int L, int nfeats, int njoints,
+                                                      float* __restrict__ joints) {
+  __shared__ float ang[SA_MAXL], px[SA_MAXL], pz[SA_MAXL], py[SA_MAXL];
+  const int b = blockIdx.x;
+  const float* f = feats + static_cast<long>(b) * L * nfeats;
+  auto feat = [&](int t, int c) { return f[static_cast<long>(t) * nfeats + c] * stdv[c] + mean[c]; };
+  // r_rot_ang[t] = sum_{u<t} rot_vel[u]  (sequential in fp32 to follow torch.cumsum's left-to-right order)
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int t = 0; t < L; ++t) {
+      if (t > 0) a += feat(t - 1, 0);
+      ang[t] = a;
+    }
+  }
+  __syncthreads();
+  // rotated root velocity, then cumsum
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    float vx = 0.f, vz = 0.f;
+    if (t > 0) {
+      vx = feat(t - 1, 1);
+      vz = feat(t - 1, 2);
+    }
+    // qrot with q_inv = (cos a, 0, -sin a, 0), v = (vx, 0, vz)
+    const float w = cosf(ang[t]), qy = -sinf(ang[t]);
+    const float uvx = qy * vz, uvz = -qy * vx;          // cross((0,qy,0), v)
+    const float uuvx = qy * uvz, uuvz = -qy * uvx;      // cross((0,qy,0), uv)
+    px[t] = vx + 2.f * (w * uvx + uuvx);
+    pz[t] = vz + 2.f * (w * uvz + uuvz);
+    py[t] = feat(t, 3);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sx = 0.f, sz = 0.f;
+    for (int t = 0; t < L; ++t) {
+      sx += px[t];
+      sz += pz[t];
+      px[t] = sx;
+      pz[t] = sz;
+    }
+  }
+  __syncthreads();
+  float* out = joints + static_cast<long>(b) * L * njoints * 3;
+  for (int i = threadIdx.x; i < L * njoints; i += blockDim.x) {
+    const int t = i / njoints, j = i % njoints;
+    float x, y, z;
+    if (j == 0) {
+      x = px[t]; y = py[t]; z = pz[t];
+    } else {
+      const float vx = feat(t, 4 + (j - 1) * 3), vy = feat(t, 5 + (j - 1) * 3), vz = feat(t, 6 + (j - 1) * 3);
+      const float w = cosf(ang[t]), qy = -sinf(ang[t]);
+      const float uvx = qy * vz, uvz = -qy * vx;
+      const float uuvx = qy * uvz, uuvz = -qy * uvx;
+      x = vx + 2.f * (w * uvx + uuvx) + px[t];
+      y = vy;
+      z = vz + 2.f * (w * uvz + uuvz) + pz[t];
+    }
+    out[static_cast<long>(i) * 3 + 0] = x;
+    out[static_cast<long>(i) * 3 + 1] = y;
+    out[static_cast<long>(i) * 3 + 2] = z;
+  }
+}

@@ -1,0 +1,1066 @@
+// C-ABI implementation (include/ladiff_b200.h): handle, weight packing, plans (workspace + CUDA graph) and the
+// orchestration of the hoisted, ragged sampling path described in DESIGN.md.
+#include "../../include/ladiff_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "linear.cuh"
+
+namespace {
+
+constexpr int NL = 9;  // layers (4 input + middle + 4 output blocks)
+
+// ------------------------------------------------------------------------------------------------
+struct Err {
+  std::string msg;
+  int set(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    msg = buf;
+    return code;
+  }
+};
+thread_local std::string g_create_error;
+
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return h->err.set(LADIFF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CKS(expr)                \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != LADIFF_OK) return _s; \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Raw {
+  float* dev = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// One packed nn.Linear: fp32 transposed copy for the SIMT backend, zero-padded bf16 hi/lo planes + TMA map for tcgen05.
+struct Weight {
+  int N = 0, K = 0, n_pad = 0;
+  float* Wt = nullptr;
+  __nv_bfloat16* pl = nullptr;
+  float* bias = nullptr;
+  CUtensorMap map;
+};
+
+struct ActBuf {
+  Act act{nullptr, nullptr, 0, 0};
+  CUtensorMap map;
+  bool has_map = false;
+};
+
+struct Arena {
+  std::vector<void*> blocks;
+  ~Arena() {
+    for (void* p : blocks) cudaFree(p);
+  }
+  cudaError_t alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e == cudaSuccess) blocks.push_back(*p);
+    return e;
+  }
+};
+
+struct DenLayerW {
+  Weight qkv, out, ff1, ff2, ca_value, ca_out, gff1, gff2, ffn_out;
+  float *n1g, *n1b, *n2g, *n2b, *ca_tn_g, *ca_tn_b, *ca_sn_g, *ca_sn_b, *ffn_sn_g, *ffn_sn_b;
+};
+struct DecLayerW {
+  Weight qkv, out, q2, out2, ff1, ff2;
+  float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
+};
+
+struct DenoisePlan;
+struct DecodePlan;
+
+}  // namespace
+
+struct ladiff_handle {
+  ladiff_config cfg;
+  Err err;
+  EncodeTiledFn encode = nullptr;
+  int device = 0;
+  int64_t launches = 0;
+  std::map<std::string, Raw> raw;
+  Arena warena;  // packed weights
+  bool den_ready = false, dec_ready = false;
+  // denoiser
+  DenLayerW den[NL];
+  Weight den_skip[4], time1, time2, embproj, timekv_all, textkv_all, mod_all;
+  float *den_fg = nullptr, *den_fb = nullptr, *den_pe = nullptr;
+  // decoder
+  DecLayerW dec[NL];
+  Weight dec_skip[4], dec_final, memkv_all;
+  float *dec_fg = nullptr, *dec_fb = nullptr, *dec_pe = nullptr;
+  std::map<std::string, std::unique_ptr<DenoisePlan>> den_plans;
+  std::map<std::string, std::unique_ptr<DecodePlan>> dec_plans;
+  cudaStream_t cap_stream = nullptr;
+};
+
+namespace {
+
+typedef ladiff_handle H;
+
+const char* block_name(int l) {
+  static const char* n[NL] = {"input_blocks.0", "input_blocks.1", "input_blocks.2", "input_blocks.3", "middle_block",
+                              "output_blocks.0", "output_blocks.1", "output_blocks.2", "output_blocks.3"};
+  return n[l];
+}
+
+int make_map(H* h, CUtensorMap* m, const __nv_bfloat16* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return h->err.set(LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
+                                          (unsigned long long)rows, (unsigned long long)cols);
+  return LADIFF_OK;
+}
+
+int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+int alloc_act(H* h, Arena& ar, ActBuf* b, int rows, int ld, bool f32, bool planes) {
+  b->act.ld = ld;
+  b->act.rows_alloc = roundup(rows < 1 ? 1 : rows, 128);
+  b->act.f32 = nullptr;
+  b->act.pl = nullptr;
+  b->has_map = false;
+  const size_t n = static_cast<size_t>(b->act.rows_alloc) * ld;
+  if (f32) {
+    CK(ar.alloc(reinterpret_cast<void**>(&b->act.f32), n * sizeof(float)));
+    CK(cudaMemset(b->act.f32, 0, n * sizeof(float)));
+  }
+  if (planes) {
+    CK(ar.alloc(reinterpret_cast<void**>(&b->act.pl), 2 * n * sizeof(__nv_bfloat16)));
+    CK(cudaMemset(b->act.pl, 0, 2 * n * sizeof(__nv_bfloat16)));
+    CKS(make_map(h, &b->map, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 128));
+    b->has_map = true;
+  }
+  return LADIFF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launching the fused linear
+struct LinCall {
+  const ActBuf* A = nullptr;
+  const ActBuf* A2 = nullptr;  // second K source (skip merge)
+  const Weight* W = nullptr;
+  int M_max = 0;
+  const int* M_dev = nullptr;
+  int epi = EPI_BIAS;
+  const float* res = nullptr;
+  int ldres = 256;
+  const float *ln_g = nullptr, *ln_b = nullptr, *mod = nullptr, *addv = nullptr;
+  const int* add_idx = nullptr;
+  int ld_add = 256;
+  const int* row_map = nullptr;
+  Act out{nullptr, nullptr, 0, 0};
+  int out_planes = 0;
+  int n_store = -1;
+};
+
+template <int BN, int NS>
+int launch_tc(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int tiles_m) {
+  using Cfg = TcCfg<BN, NS>;
+  dim3 grid(tiles_m, (c.W->N + BN - 1) / BN);
+  k_linear_tc<BN, NS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(c.A->map, c.A2 ? c.A2->map : c.A->map, c.W->map, a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return LADIFF_OK;
+}
+
+int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
+  LinArgs a;
+  memset(&a, 0, sizeof(a));
+  const Weight& W = *c.W;
+  a.M_max = c.M_max;
+  a.M_dev = c.M_dev;
+  a.N = W.N;
+  a.K = W.K;
+  a.K1 = c.A2 ? c.A->act.ld : W.K;
+  if (c.A2 && (c.A->act.ld + c.A2->act.ld != W.K)) return h->err.set(LADIFF_ERR_INVALID, "two-source linear: K mismatch");
+  if (!c.A2 && c.A->act.ld != W.K) return h->err.set(LADIFF_ERR_INVALID, "linear: A width %d != K %d", c.A->act.ld, W.K);
+  a.A = c.A->act.f32;
+  a.lda = c.A->act.ld;
+  a.A2 = c.A2 ? c.A2->act.f32 : nullptr;
+  a.lda2 = c.A2 ? c.A2->act.ld : 0;
+  a.Wt = W.Wt;
+  a.ldw = W.N;
+  a.bias = W.bias;
+  a.epi = c.epi;
+  a.res = c.res;
+  a.ldres = c.ldres;
+  a.ln_g = c.ln_g;
+  a.ln_b = c.ln_b;
+  a.mod = c.mod;
+  a.addv = c.addv;
+  a.add_idx = c.add_idx;
+  a.ld_add = c.ld_add;
+  a.row_map = c.row_map;
+  a.out = c.out;
+  a.out_planes = c.out_planes;
+  a.n_store = c.n_store < 0 ? W.N : c.n_store;
+  const bool ln = (c.epi == EPI_LN || c.epi == EPI_LN_MOD_SILU);
+  if (ln && W.N != 256) return h->err.set(LADIFF_ERR_INVALID, "LayerNorm epilogue needs N == 256");
+  if (c.M_max <= 0) return LADIFF_OK;
+  if (mode == LADIFF_MODE_FP32) {
+    if (!a.A || (c.A2 && !a.A2)) return h->err.set(LADIFF_ERR_STATE, "fp32 linear: missing fp32 operand");
+    if (c.M_max >= 4096) {
+      dim3 grid((c.M_max + 31) / 32, (W.N + 255) / 256);
+      k_linear_simt<4><<<grid, 256, 0, st>>>(a);
+    } else {
+      dim3 grid((c.M_max + 15) / 16, (W.N + 255) / 256);
+      k_linear_simt<2><<<grid, 256, 0, st>>>(a);
+    }
+    CK(cudaGetLastError());
+    h->launches++;
+    return LADIFF_OK;
+  }
+  if (!c.A->has_map || (c.A2 && !c.A2->has_map)) return h->err.set(LADIFF_ERR_STATE, "tensor-core linear: operand has no bf16 planes");
+  if (W.K % 64 != 0 || a.K1 % 64 != 0) return h->err.set(LADIFF_ERR_INVALID, "tensor-core linear: K must be a multiple of 64");
+  a.a_plane_rows = c.A->act.rows_alloc;
+  a.a2_plane_rows = c.A2 ? c.A2->act.rows_alloc : 0;
+  a.w_plane_rows = W.n_pad;
+  const int tiles_m = (c.M_max + 127) / 128;
+  int bn = 256;
+  if (!ln) {
+    const int sm2 = 2 * 148;
+    if (tiles_m * ((W.N + 63) / 64) <= sm2) bn = 64;
+    else if (tiles_m * ((W.N + 127) / 128) <= sm2) bn = 128;
+  }
+  const bool split = (mode == LADIFF_MODE_BF16X3);
+  if (bn == 256) return split ? launch_tc<256, 2>(h, st, c, a, tiles_m) : launch_tc<256, 1>(h, st, c, a, tiles_m);
+  if (bn == 128) return split ? launch_tc<128, 2>(h, st, c, a, tiles_m) : launch_tc<128, 1>(h, st, c, a, tiles_m);
+  return split ? launch_tc<64, 2>(h, st, c, a, tiles_m) : launch_tc<64, 1>(h, st, c, a, tiles_m);
+}
+
+#define LAUNCH(kernel, grid, block, smem, st, ...)  \
+  do {                                              \
+    kernel<<<grid, block, smem, st>>>(__VA_ARGS__); \
+    CK(cudaGetLastError());                         \
+    h->launches++;                                  \
+  } while (0)
+
+inline unsigned cdiv(long a, long b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// weights
+int get_raw(H* h, const std::string& name, std::initializer_list<int64_t> shape, const Raw** out) {
+  auto it = h->raw.find(name);
+  if (it == h->raw.end()) return h->err.set(LADIFF_ERR_WEIGHTS, "missing weight '%s'", name.c_str());
+  const Raw& r = it->second;
+  if (r.shape.size() != shape.size() || !std::equal(shape.begin(), shape.end(), r.shape.begin())) {
+    std::string got;
+    for (auto s : r.shape) got += std::to_string(s) + ",";
+    std::string want;
+    for (auto s : shape) want += std::to_string(s) + ",";
+    return h->err.set(LADIFF_ERR_WEIGHTS, "size mismatch for %s: got [%s] expected [%s]", name.c_str(), got.c_str(), want.c_str());
+  }
+  *out = &r;
+  return LADIFF_OK;
+}
+
+// Packs rows [row0, row0+N) of a [*, K] fp32 matrix (+ bias slice) into a Weight.
+int pack_weight(H* h, Arena& ar, cudaStream_t st, Weight* w, const float* W_dev, int ldw, int N, int K, const float* bias_dev) {
+  w->N = N;
+  w->K = K;
+  w->n_pad = roundup(N, 256);
+  CK(ar.alloc(reinterpret_cast<void**>(&w->Wt), static_cast<size_t>(N) * K * sizeof(float)));
+  CK(ar.alloc(reinterpret_cast<void**>(&w->pl), 2ull * w->n_pad * K * sizeof(__nv_bfloat16)));
+  w->bias = nullptr;
+  if (bias_dev) {
+    CK(ar.alloc(reinterpret_cast<void**>(&w->bias), N * sizeof(float)));
+    CK(cudaMemcpyAsync(w->bias, bias_dev, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  LAUNCH(k_pack_weight, cdiv(static_cast<long>(w->n_pad) * K, 256), 256, 0, st, W_dev, ldw, N, K, w->n_pad, w->Wt, w->pl);
+  if (K % 64 == 0) CKS(make_map(h, &w->map, w->pl, 2ull * w->n_pad, K, K, 64));
+  return LADIFF_OK;
+}
+
+int pack_linear(H* h, cudaStream_t st, Weight* w, const std::string& prefix, int N, int K) {
+  const Raw *W, *b;
+  CKS(get_raw(h, prefix + ".weight", {N, K}, &W));
+  CKS(get_raw(h, prefix + ".bias", {N}, &b));
+  return pack_weight(h, h->warena, st, w, W->dev, K, N, K, b->dev);
+}
+
+int get_vec(H* h, const std::string& name, int n, float** out) {
+  const Raw* r;
+  CKS(get_raw(h, name, {n}, &r));
+  *out = r->dev;
+  return LADIFF_OK;
+}
+
+// concatenates row-slices [row0,row0+rows) of `count` same-shaped matrices (+ bias slices) and packs them as one Weight
+int pack_concat(H* h, cudaStream_t st, Weight* w, const std::vector<std::pair<const Raw*, const Raw*>>& parts, int row0,
+                int rows, int K) {
+  const int N = rows * static_cast<int>(parts.size());
+  float *tmpW = nullptr, *tmpB = nullptr;
+  CK(cudaMalloc(&tmpW, static_cast<size_t>(N) * K * sizeof(float)));
+  CK(cudaMalloc(&tmpB, N * sizeof(float)));
+  for (size_t i = 0; i < parts.size(); ++i) {
+    CK(cudaMemcpyAsync(tmpW + i * rows * K, parts[i].first->dev + static_cast<size_t>(row0) * K,
+                       static_cast<size_t>(rows) * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(tmpB + i * rows, parts[i].second->dev + row0, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  int s = pack_weight(h, h->warena, st, w, tmpW, K, N, K, tmpB);
+  CK(cudaStreamSynchronize(st));
+  cudaFree(tmpW);
+  cudaFree(tmpB);
+  return s;
+}
+
+int finalize_denoiser(H* h, cudaStream_t st) {
+  const int D = 256;
+  const std::string P = "denoiser.";
+  CKS(pack_linear(h, st, &h->time1, P + "time_embedding.linear_1", D, 768));
+  CKS(pack_linear(h, st, &h->time2, P + "time_embedding.linear_2", D, D));
+  CKS(pack_linear(h, st, &h->embproj, P + "emb_proj.1", D, 768));
+  const Raw* pe;
+  CKS(get_raw(h, P + "query_pos.pe", {500, 1, D}, &pe));
+  h->den_pe = pe->dev;
+  CKS(get_vec(h, P + "encoder.norm.weight", D, &h->den_fg));
+  CKS(get_vec(h, P + "encoder.norm.bias", D, &h->den_fb));
+  std::vector<std::pair<const Raw*, const Raw*>> inproj, mods;
+  for (int l = 0; l < NL; ++l) {
+    const std::string L = P + "encoder." + block_name(l) + ".";
+    DenLayerW& w = h->den[l];
+    const Raw *ipw, *ipb;
+    CKS(get_raw(h, L + "sa_block.self_attn.in_proj_weight", {3 * D, D}, &ipw));
+    CKS(get_raw(h, L + "sa_block.self_attn.in_proj_bias", {3 * D}, &ipb));
+    CKS(pack_weight(h, h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
+    inproj.push_back({ipw, ipb});
+    CKS(pack_linear(h, st, &w.out, L + "sa_block.self_attn.out_proj", D, D));
+    CKS(pack_linear(h, st, &w.ff1, L + "sa_block.linear1", 1024, D));
+    CKS(pack_linear(h, st, &w.ff2, L + "sa_block.linear2", D, 1024));
+    CKS(get_vec(h, L + "sa_block.norm1.weight", D, &w.n1g));
+    CKS(get_vec(h, L + "sa_block.norm1.bias", D, &w.n1b));
+    CKS(get_vec(h, L + "sa_block.norm2.weight", D, &w.n2g));
+    CKS(get_vec(h, L + "sa_block.norm2.bias", D, &w.n2b));
+    // ca_block: with one text token softmax over tokens == 1, so query/key/norm are mathematically dead
+    // (mdiff_transformer.py:231-245); they must still be present in the state_dict like in the reference.
+    const Raw* dead;
+    CKS(get_raw(h, L + "ca_block.query.weight", {D, D}, &dead));
+    CKS(get_raw(h, L + "ca_block.key.weight", {D, D}, &dead));
+    CKS(pack_linear(h, st, &w.ca_value, L + "ca_block.value", D, D));
+    CKS(get_vec(h, L + "ca_block.text_norm.weight", D, &w.ca_tn_g));
+    CKS(get_vec(h, L + "ca_block.text_norm.bias", D, &w.ca_tn_b));
+    CKS(get_vec(h, L + "ca_block.proj_out.norm.weight", D, &w.ca_sn_g));
+    CKS(get_vec(h, L + "ca_block.proj_out.norm.bias", D, &w.ca_sn_b));
+    CKS(pack_linear(h, st, &w.ca_out, L + "ca_block.proj_out.out_layers.2", D, D));
+    CKS(pack_linear(h, st, &w.gff1, L + "ffn.linear1", h->cfg.ff_size, D));
+    CKS(pack_linear(h, st, &w.gff2, L + "ffn.linear2", D, h->cfg.ff_size));
+    CKS(get_vec(h, L + "ffn.proj_out.norm.weight", D, &w.ffn_sn_g));
+    CKS(get_vec(h, L + "ffn.proj_out.norm.bias", D, &w.ffn_sn_b));
+    CKS(pack_linear(h, st, &w.ffn_out, L + "ffn.proj_out.out_layers.2", D, D));
+    const Raw *cw, *cb, *fw, *fb;
+    CKS(get_raw(h, L + "ca_block.proj_out.emb_layers.1.weight", {2 * D, D}, &cw));
+    CKS(get_raw(h, L + "ca_block.proj_out.emb_layers.1.bias", {2 * D}, &cb));
+    CKS(get_raw(h, L + "ffn.proj_out.emb_layers.1.weight", {2 * D, D}, &fw));
+    CKS(get_raw(h, L + "ffn.proj_out.emb_layers.1.bias", {2 * D}, &fb));
+    mods.push_back({cw, cb});
+    mods.push_back({fw, fb});
+  }
+  for (int i = 0; i < 4; ++i) CKS(pack_linear(h, st, &h->den_skip[i], P + "encoder.linear_blocks." + std::to_string(i), D, 2 * D));
+  // K/V rows of every layer's in_proj: the conditioning tokens are step- or prompt-invariant
+  CKS(pack_concat(h, st, &h->timekv_all, inproj, D, 2 * D, D));
+  h->textkv_all = h->timekv_all;  // same matrix, applied to the text projection
+  CKS(pack_concat(h, st, &h->mod_all, mods, 0, 2 * D, D));
+  h->den_ready = true;
+  return LADIFF_OK;
+}
+
+int finalize_decoder(H* h, cudaStream_t st) {
+  const int D = 256;
+  const std::string P = "vae.";
+  const Raw* pe;
+  CKS(get_raw(h, P + "query_pos_decoder.pe", {500, 1, D}, &pe));
+  h->dec_pe = pe->dev;
+  CKS(get_vec(h, P + "decoder.norm.weight", D, &h->dec_fg));
+  CKS(get_vec(h, P + "decoder.norm.bias", D, &h->dec_fb));
+  std::vector<std::pair<const Raw*, const Raw*>> memproj;
+  for (int l = 0; l < NL; ++l) {
+    const std::string L = P + "decoder." + block_name(l) + ".";
+    DecLayerW& w = h->dec[l];
+    const Raw *ipw, *ipb, *mw, *mb;
+    CKS(get_raw(h, L + "self_attn.in_proj_weight", {3 * D, D}, &ipw));
+    CKS(get_raw(h, L + "self_attn.in_proj_bias", {3 * D}, &ipb));
+    CKS(pack_weight(h, h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
+    CKS(pack_linear(h, st, &w.out, L + "self_attn.out_proj", D, D));
+    CKS(get_raw(h, L + "multihead_attn.in_proj_weight", {3 * D, D}, &mw));
+    CKS(get_raw(h, L + "multihead_attn.in_proj_bias", {3 * D}, &mb));
+    CKS(pack_weight(h, h->warena, st, &w.q2, mw->dev, D, D, D, mb->dev));
+    memproj.push_back({mw, mb});
+    CKS(pack_linear(h, st, &w.out2, L + "multihead_attn.out_proj", D, D));
+    CKS(pack_linear(h, st, &w.ff1, L + "linear1", h->cfg.ff_size, D));
+    CKS(pack_linear(h, st, &w.ff2, L + "linear2", D, h->cfg.ff_size));
+    CKS(get_vec(h, L + "norm1.weight", D, &w.n1g));
+    CKS(get_vec(h, L + "norm1.bias", D, &w.n1b));
+    CKS(get_vec(h, L + "norm2.weight", D, &w.n2g));
+    CKS(get_vec(h, L + "norm2.bias", D, &w.n2b));
+    CKS(get_vec(h, L + "norm3.weight", D, &w.n3g));
+    CKS(get_vec(h, L + "norm3.bias", D, &w.n3b));
+  }
+  for (int i = 0; i < 4; ++i) CKS(pack_linear(h, st, &h->dec_skip[i], P + "decoder.linear_blocks." + std::to_string(i), D, 2 * D));
+  CKS(pack_concat(h, st, &h->memkv_all, memproj, D, 2 * D, D));
+  CKS(pack_linear(h, st, &h->dec_final, P + "final_layer", h->cfg.nfeats, D));
+  h->dec_ready = true;
+  return LADIFF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// denoiser plan
+struct DenoisePlan {
+  Arena ar;
+  int S = 0, B = 0, n = 0, mode = 0, T = 0, Rmax = 0;
+  bool cfg = false;
+  int planes = 0;  // bf16 planes written by producers: 0 fp32 mode, 1 bf16, 2 bf16x3
+  // meta
+  int *cnt = nullptr, *off = nullptr, *R = nullptr, *row_seq = nullptr, *row_t = nullptr, *ts = nullptr;
+  float* coef = nullptr;  // [n][2]
+  std::vector<int> cached_ts;
+  std::vector<float> cached_coef;
+  // inputs staged in the workspace so the captured graph has fixed addresses
+  float *text768 = nullptr, *lat = nullptr;
+  // time side
+  ActBuf sin, t1, temb, st;
+  float *timekv = nullptr, *mod = nullptr;
+  // text side
+  ActBuf trelu, textp, tn, ca_a;
+  float *textkv = nullptr, *lny = nullptr, *delta = nullptr;
+  // activations
+  ActBuf xin, xa, xb, x1, x3, skip[4], a, hbuf, sbuf;
+  float* qkv = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t graph_launches = 0;
+  ~DenoisePlan() {
+    if (exec) cudaGraphExecDestroy(exec);
+  }
+};
+
+Act f32_only(float* p, int ld) { return Act{p, nullptr, ld, 0}; }
+
+int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg) {
+  p->S = S;
+  p->B = cfg ? S / 2 : 0;
+  p->n = n;
+  p->mode = mode;
+  p->cfg = cfg;
+  p->T = h->cfg.max_it;
+  p->Rmax = S * p->T;
+  p->planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
+  const bool tcm = mode != LADIFF_MODE_FP32, f = !tcm;
+  Arena& ar = p->ar;
+  const int R = p->Rmax;
+  CK(ar.alloc((void**)&p->cnt, S * sizeof(int)));
+  CK(ar.alloc((void**)&p->off, (S + 1) * sizeof(int)));
+  CK(ar.alloc((void**)&p->R, sizeof(int)));
+  CK(ar.alloc((void**)&p->row_seq, R * sizeof(int)));
+  CK(ar.alloc((void**)&p->row_t, R * sizeof(int)));
+  CK(ar.alloc((void**)&p->ts, n * sizeof(int)));
+  CK(ar.alloc((void**)&p->coef, 2 * n * sizeof(float)));
+  CK(ar.alloc((void**)&p->text768, static_cast<size_t>(S) * 768 * sizeof(float)));
+  if (cfg) CK(ar.alloc((void**)&p->lat, static_cast<size_t>(p->B) * p->T * 256 * sizeof(float)));
+  CKS(alloc_act(h, ar, &p->sin, n, 768, f, tcm));
+  CKS(alloc_act(h, ar, &p->t1, n, 256, f, tcm));
+  CKS(alloc_act(h, ar, &p->temb, n, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->st, n, 256, f, tcm));
+  CK(ar.alloc((void**)&p->timekv, static_cast<size_t>(n) * NL * 512 * sizeof(float)));
+  CK(ar.alloc((void**)&p->mod, static_cast<size_t>(n) * NL * 1024 * sizeof(float)));
+  CKS(alloc_act(h, ar, &p->trelu, S, 768, f, tcm));
+  CKS(alloc_act(h, ar, &p->textp, S, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->tn, S, 256, f, tcm));
+  CKS(alloc_act(h, ar, &p->ca_a, n * S, 256, f, tcm));
+  CK(ar.alloc((void**)&p->textkv, static_cast<size_t>(S) * NL * 512 * sizeof(float)));
+  CK(ar.alloc((void**)&p->lny, static_cast<size_t>(NL) * S * 256 * sizeof(float)));
+  CK(ar.alloc((void**)&p->delta, static_cast<size_t>(NL) * n * S * 256 * sizeof(float)));
+  CKS(alloc_act(h, ar, &p->xin, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->xa, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->xb, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->x1, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->x3, R, 256, true, tcm));
+  for (int i = 0; i < 4; ++i) CKS(alloc_act(h, ar, &p->skip[i], R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->a, R, 256, f, tcm));
+  CKS(alloc_act(h, ar, &p->hbuf, R, 1024, f, tcm));
+  CKS(alloc_act(h, ar, &p->sbuf, R, 256, f, tcm));
+  CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * 768 * sizeof(float)));
+  return LADIFF_OK;
+}
+
+// time tables: depend on (timesteps, weights) only -> cached across calls (SURVEY.md 8a hoist table)
+int enqueue_time_tables(H* h, DenoisePlan* p, cudaStream_t st) {
+  const int n = p->n, mode = p->mode, pl = p->planes;
+  LAUNCH(k_sinus_embed, cdiv(n * 768, 256), 256, 0, st, p->ts, n, p->sin.act, pl);
+  LinCall c;
+  c.A = &p->sin; c.W = &h->time1; c.M_max = n; c.epi = EPI_SILU; c.out = p->t1.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->t1; c.W = &h->time2; c.M_max = n; c.out = p->temb.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  LAUNCH(k_unary, cdiv(n * 256, 256), 256, 0, st, p->temb.act.f32, 256, n, 256, (int)U_SILU, p->st.act, pl);
+  c = LinCall(); c.A = &p->temb; c.W = &h->timekv_all; c.M_max = n; c.out = f32_only(p->timekv, NL * 512);
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->st; c.W = &h->mod_all; c.M_max = n; c.out = f32_only(p->mod, NL * 1024);
+  CKS(launch_linear(h, st, mode, c));
+  return LADIFF_OK;
+}
+
+// text tables + the hoisted ca_block contribution for every (step, layer, sequence)
+int enqueue_text_tables(H* h, DenoisePlan* p, cudaStream_t st) {
+  const int S = p->S, n = p->n, mode = p->mode, pl = p->planes;
+  LAUNCH(k_unary, cdiv(static_cast<long>(S) * 768, 256), 256, 0, st, p->text768, 768, S, 768, (int)U_RELU, p->trelu.act, pl);
+  LinCall c;
+  c.A = &p->trelu; c.W = &h->embproj; c.M_max = S; c.out = p->textp.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->textp; c.W = &h->textkv_all; c.M_max = S; c.out = f32_only(p->textkv, NL * 512);
+  CKS(launch_linear(h, st, mode, c));
+  for (int l = 0; l < NL; ++l) {
+    const DenLayerW& w = h->den[l];
+    LAUNCH(k_layernorm256, cdiv(static_cast<long>(S) * 32, 256), 256, 0, st, p->textp.act.f32, 256, S, (const int*)nullptr,
+           w.ca_tn_g, w.ca_tn_b, p->tn.act, pl);
+    float* lny = p->lny + static_cast<size_t>(l) * S * 256;
+    c = LinCall(); c.A = &p->tn; c.W = &w.ca_value; c.M_max = S; c.epi = EPI_LN; c.ln_g = w.ca_sn_g; c.ln_b = w.ca_sn_b;
+    c.out = f32_only(lny, 256);
+    CKS(launch_linear(h, st, mode, c));
+    LAUNCH(k_ca_prologue, cdiv(static_cast<long>(n) * S * 256, 256), 256, 0, st, lny, 256, p->mod + l * 1024, NL * 1024, n, S,
+           p->ca_a.act, pl);
+    c = LinCall(); c.A = &p->ca_a; c.W = &w.ca_out; c.M_max = n * S;
+    c.out = f32_only(p->delta + static_cast<size_t>(l) * n * S * 256, 256);
+    CKS(launch_linear(h, st, mode, c));
+  }
+  return LADIFF_OK;
+}
+
+int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, const ActBuf& in, const ActBuf& out) {
+  const DenLayerW& w = h->den[l];
+  const int mode = p->mode, pl = p->planes, R = p->Rmax, S = p->S, n = p->n;
+  LinCall c;
+  c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
+  CKS(launch_linear(h, st, mode, c));
+  LAUNCH(k_attn_small<8>, cdiv(static_cast<long>(S) * 4 * 32, 256), 256, 0, st, p->qkv, p->off, S, p->textkv + l * 512, NL * 512,
+         p->timekv + static_cast<size_t>(step) * NL * 512 + l * 512, p->a.act, pl);
+  c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = in.act.f32;
+  c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = p->x1.act.f32;
+  c.ln_g = w.n2g; c.ln_b = w.n2b;
+  c.addv = p->delta + (static_cast<size_t>(l) * n + step) * S * 256; c.add_idx = p->row_seq; c.ld_add = 256;
+  c.out = p->x3.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->x3; c.W = &w.gff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_GELU; c.out = p->hbuf.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->hbuf; c.W = &w.gff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN_MOD_SILU;
+  c.ln_g = w.ffn_sn_g; c.ln_b = w.ffn_sn_b; c.mod = p->mod + static_cast<size_t>(step) * NL * 1024 + l * 1024 + 512;
+  c.out = p->sbuf.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->sbuf; c.W = &w.ffn_out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RES; c.res = p->x3.act.f32;
+  c.out = out.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  return LADIFF_OK;
+}
+
+// SkipTransformerEncoder wiring (operator/cross_attention.py:69-85); tokens end up in p->xa
+int enqueue_den_tokens(H* h, DenoisePlan* p, cudaStream_t st, int step) {
+  const ActBuf* x = &p->xin;
+  for (int i = 0; i < 4; ++i) {
+    CKS(enqueue_den_layer(h, p, st, i, step, *x, p->skip[i]));
+    x = &p->skip[i];
+  }
+  CKS(enqueue_den_layer(h, p, st, 4, step, *x, p->xa));
+  for (int i = 0; i < 4; ++i) {
+    LinCall c;
+    c.A = &p->xa; c.A2 = &p->skip[3 - i]; c.W = &h->den_skip[i]; c.M_max = p->Rmax; c.M_dev = p->R;
+    c.out = p->xb.act; c.out_planes = p->planes;
+    CKS(launch_linear(h, st, p->mode, c));
+    CKS(enqueue_den_layer(h, p, st, 5 + i, step, p->xb, p->xa));
+  }
+  return LADIFF_OK;
+}
+
+int enqueue_meta(H* h, cudaStream_t st, const int* cnt_host, int S, int* cnt, int* off, int* R, int* row_seq, int* row_t,
+                 int* row_dst, int dst_stride) {
+  CK(cudaMemcpyAsync(cnt, cnt_host, S * sizeof(int), cudaMemcpyHostToDevice, st));
+  LAUNCH(k_scan_counts, 1, 1024, 0, st, cnt, S, off, R);
+  LAUNCH(k_fill_rows, cdiv(static_cast<long>(S) * 32, 256), 256, 0, st, off, S, row_seq, row_t, row_dst, dst_stride);
+  return LADIFF_OK;
+}
+
+int enqueue_reverse_body(H* h, DenoisePlan* p, cudaStream_t st, float guidance) {
+  CKS(enqueue_text_tables(h, p, st));
+  LAUNCH(k_pack_x, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, p->lat, p->B, p->T, h->den_pe, p->row_seq, p->row_t, p->R,
+         p->xin.act, p->planes);
+  for (int step = 0; step < p->n; ++step) {
+    CKS(enqueue_den_tokens(h, p, st, step));
+    LAUNCH(k_cfg_ddim, cdiv(static_cast<long>(p->B) * p->T * 32, 256), 256, 0, st, p->xa.act.f32, p->off, p->B, p->T, h->den_fg, h->den_fb,
+           p->coef + 2 * step, guidance, p->lat, h->den_pe, p->xin.act, p->planes);
+  }
+  return LADIFF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder plan
+struct DecodePlan {
+  Arena ar;
+  int B = 0, mode = 0, T = 0, Lmax = 0, Rmax = 0, Mmax = 0, planes = 0;
+  int *cnt = nullptr, *foff = nullptr, *Rf = nullptr, *frow_seq = nullptr, *frow_t = nullptr, *frow_dst = nullptr;
+  int *mcnt = nullptr, *moff = nullptr, *Rm = nullptr, *mrow_seq = nullptr, *mrow_t = nullptr;
+  float* z = nullptr;  // staged [T,B,256]
+  ActBuf zrows, x0, xa, xb, x1, x2, skip[4], a, hbuf, xn;
+  float *qkv = nullptr, *q2 = nullptr, *memkv = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t graph_launches = 0;
+  ~DecodePlan() {
+    if (exec) cudaGraphExecDestroy(exec);
+  }
+};
+
+int build_decode_plan(H* h, DecodePlan* p, int B, int mode) {
+  p->B = B;
+  p->mode = mode;
+  p->T = h->cfg.max_it;
+  p->Lmax = h->cfg.max_frames;
+  p->Rmax = B * p->Lmax;
+  p->Mmax = B * p->T;
+  p->planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
+  const bool tcm = mode != LADIFF_MODE_FP32, f = !tcm;
+  Arena& ar = p->ar;
+  const int R = p->Rmax, M = p->Mmax;
+  CK(ar.alloc((void**)&p->cnt, B * sizeof(int)));
+  CK(ar.alloc((void**)&p->foff, (B + 1) * sizeof(int)));
+  CK(ar.alloc((void**)&p->Rf, sizeof(int)));
+  CK(ar.alloc((void**)&p->frow_seq, R * sizeof(int)));
+  CK(ar.alloc((void**)&p->frow_t, R * sizeof(int)));
+  CK(ar.alloc((void**)&p->frow_dst, R * sizeof(int)));
+  CK(ar.alloc((void**)&p->mcnt, B * sizeof(int)));
+  CK(ar.alloc((void**)&p->moff, (B + 1) * sizeof(int)));
+  CK(ar.alloc((void**)&p->Rm, sizeof(int)));
+  CK(ar.alloc((void**)&p->mrow_seq, M * sizeof(int)));
+  CK(ar.alloc((void**)&p->mrow_t, M * sizeof(int)));
+  CK(ar.alloc((void**)&p->z, static_cast<size_t>(M) * 256 * sizeof(float)));
+  CKS(alloc_act(h, ar, &p->zrows, M, 256, f, tcm));
+  CKS(alloc_act(h, ar, &p->x0, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->xa, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->xb, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->x1, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->x2, R, 256, true, tcm));
+  for (int i = 0; i < 4; ++i) CKS(alloc_act(h, ar, &p->skip[i], R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->a, R, 256, f, tcm));
+  CKS(alloc_act(h, ar, &p->hbuf, R, 1024, f, tcm));
+  CKS(alloc_act(h, ar, &p->xn, R, 256, f, tcm));
+  CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * 768 * sizeof(float)));
+  CK(ar.alloc((void**)&p->q2, static_cast<size_t>(roundup(R, 128)) * 256 * sizeof(float)));
+  CK(ar.alloc((void**)&p->memkv, static_cast<size_t>(roundup(M, 128)) * NL * 512 * sizeof(float)));
+  return LADIFF_OK;
+}
+
+int enqueue_dec_layer(H* h, DecodePlan* p, cudaStream_t st, int l, const ActBuf& in, const ActBuf& out) {
+  const DecLayerW& w = h->dec[l];
+  const int mode = p->mode, pl = p->planes, R = p->Rmax;
+  LinCall c;
+  c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->Rf; c.out = f32_only(p->qkv, 768);
+  CKS(launch_linear(h, st, mode, c));
+  {
+    dim3 grid((p->Lmax + SA_QB - 1) / SA_QB, 4, p->B);
+    LAUNCH(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, p->qkv, p->foff, p->a.act, pl);
+  }
+  c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = in.act.f32;
+  c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->x1; c.W = &w.q2; c.M_max = R; c.M_dev = p->Rf; c.out = f32_only(p->q2, 256);
+  CKS(launch_linear(h, st, mode, c));
+  LAUNCH(k_attn_cross<8>, cdiv(static_cast<long>(R) * 32, 256), 256, 0, st, p->q2, p->memkv, NL * 512, l * 512, p->frow_seq, p->moff, p->Rf,
+         p->a.act, pl);
+  c = LinCall(); c.A = &p->a; c.W = &w.out2; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = p->x1.act.f32;
+  c.ln_g = w.n2g; c.ln_b = w.n2b; c.out = p->x2.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->x2; c.W = &w.ff1; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_GELU; c.out = p->hbuf.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = p->x2.act.f32;
+  c.ln_g = w.n3g; c.ln_b = w.n3b; c.out = out.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  return LADIFF_OK;
+}
+
+// everything of vae.decode between the staged latent z and the final LayerNorm'd tokens (p->xn)
+int enqueue_decode_body(H* h, DecodePlan* p, cudaStream_t st) {
+  const int pl = p->planes, mode = p->mode;
+  LAUNCH(k_gather_z, cdiv(static_cast<long>(p->Mmax) * 256, 256), 256, 0, st, p->z, p->moff, p->B, p->T, p->zrows.act, pl);
+  LinCall c;
+  c.A = &p->zrows; c.W = &h->memkv_all; c.M_max = p->Mmax; c.M_dev = p->Rm; c.out = f32_only(p->memkv, NL * 512);
+  CKS(launch_linear(h, st, mode, c));
+  LAUNCH(k_dec_init, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, h->dec_pe, p->frow_t, p->Rf, p->x0.act, pl);
+  const ActBuf* x = &p->x0;
+  for (int i = 0; i < 4; ++i) {
+    CKS(enqueue_dec_layer(h, p, st, i, *x, p->skip[i]));
+    x = &p->skip[i];
+  }
+  CKS(enqueue_dec_layer(h, p, st, 4, *x, p->xa));
+  for (int i = 0; i < 4; ++i) {
+    c = LinCall();
+    c.A = &p->xa; c.A2 = &p->skip[3 - i]; c.W = &h->dec_skip[i]; c.M_max = p->Rmax; c.M_dev = p->Rf;
+    c.out = p->xb.act; c.out_planes = pl;
+    CKS(launch_linear(h, st, mode, c));
+    CKS(enqueue_dec_layer(h, p, st, 5 + i, p->xb, p->xa));
+  }
+  LAUNCH(k_layernorm256, cdiv(static_cast<long>(p->Rmax) * 32, 256), 256, 0, st, p->xa.act.f32, 256, p->Rmax, p->Rf, h->dec_fg, h->dec_fb,
+         p->xn.act, pl);
+  return LADIFF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph capture helper: records `body` once on the handle's private stream, replays on the caller's stream
+template <typename Body>
+int run_graphed(H* h, cudaStream_t st, cudaGraphExec_t* exec, int64_t* graph_launches, Body body) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  CK(cudaStreamIsCapturing(st, &cs));
+  if (!h->cfg.use_cuda_graph || cs != cudaStreamCaptureStatusNone) return body(st);  // plain launches (also inside a caller's capture)
+  if (!*exec) {
+    if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CK(cudaStreamSynchronize(st));  // plan tables / workspace initialisation enqueued so far
+    const int64_t before = h->launches;
+    CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int s = body(h->cap_stream);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
+    if (s != LADIFF_OK) {
+      if (g) cudaGraphDestroy(g);
+      return s;
+    }
+    if (e != cudaSuccess) return h->err.set(LADIFF_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    *graph_launches = h->launches - before;
+    h->launches = before;
+    e = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return h->err.set(LADIFF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  }
+  CK(cudaGraphLaunch(*exec, st));
+  h->launches += *graph_launches;
+  return LADIFF_OK;
+}
+
+template <int BN, int NS>
+cudaError_t set_tc_attr() {
+  return cudaFuncSetAttribute(k_linear_tc<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, NS>::SMEM_BYTES);
+}
+
+int check_mode(H* h, int mode) {
+  if (mode < 0 || mode > 2) return h->err.set(LADIFF_ERR_INVALID, "unknown mode %d", mode);
+  return LADIFF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int ladiff_abi_version(void) { return LADIFF_ABI_VERSION; }
+
+const char* ladiff_last_error(const ladiff_handle* h) { return h ? h->err.msg.c_str() : g_create_error.c_str(); }
+
+int64_t ladiff_last_launch_count(const ladiff_handle* h) { return h ? h->launches : 0; }
+
+int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
+  if (!cfg || !out) {
+    g_create_error = "null argument";
+    return LADIFF_ERR_INVALID;
+  }
+  if (cfg->num_layers != 9 || cfg->latent_dim != 256 || cfg->num_heads != 4 || cfg->ff_size != 1024 || cfg->text_dim != 768 ||
+      cfg->max_it < 1 || cfg->max_it > 8 || cfg->frame_per_latent < 1 || cfg->max_frames < 1 || cfg->max_frames > SA_MAXL ||
+      cfg->nfeats < 4 || cfg->nfeats > 1024) {
+    g_create_error = "unsupported configuration (kernels are specialised for 9 layers, width 256, 4 heads, ff 1024, text 768, "
+                     "max_it <= 8, max_frames <= 256)";
+    return LADIFF_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return LADIFF_ERR_CUDA;
+  }
+  std::unique_ptr<ladiff_handle> h(new ladiff_handle());
+  h->cfg = *cfg;
+  cudaGetDevice(&h->device);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, h->device);
+  if (e != cudaSuccess || prop.major != 10) {
+    g_create_error = "device is not sm_100 (B200): the kernels are built for sm_100a only";
+    return LADIFF_ERR_CUDA;
+  }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+  if (e != cudaSuccess || !fn) {
+    g_create_error = "cuTensorMapEncodeTiled not available from the driver";
+    return LADIFF_ERR_CUDA;
+  }
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  e = cudaFuncSetAttribute(k_attn_self, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelfAttnSmem));
+  if (e == cudaSuccess) e = set_tc_attr<256, 2>();
+  if (e == cudaSuccess) e = set_tc_attr<256, 1>();
+  if (e == cudaSuccess) e = set_tc_attr<128, 2>();
+  if (e == cudaSuccess) e = set_tc_attr<128, 1>();
+  if (e == cudaSuccess) e = set_tc_attr<64, 2>();
+  if (e == cudaSuccess) e = set_tc_attr<64, 1>();
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    return LADIFF_ERR_CUDA;
+  }
+  *out = h.release();
+  return LADIFF_OK;
+}
+
+void ladiff_destroy(ladiff_handle* h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  h->den_plans.clear();
+  h->dec_plans.clear();
+  for (auto& kv : h->raw) cudaFree(kv.second.dev);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  delete h;
+}
+
+int ladiff_set_weight(ladiff_handle* h, const char* name, const float* data_dev, const int64_t* shape, int32_t ndim, void* stream) {
+  if (!h || !name || !data_dev || !shape || ndim < 1 || ndim > 4) return h ? h->err.set(LADIFF_ERR_INVALID, "bad argument") : LADIFF_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Raw r;
+  r.shape.assign(shape, shape + ndim);
+  auto it = h->raw.find(name);
+  if (it != h->raw.end()) {
+    cudaFree(it->second.dev);
+    h->raw.erase(it);
+  }
+  CK(cudaMalloc(&r.dev, r.numel() * sizeof(float)));
+  CK(cudaMemcpyAsync(r.dev, data_dev, r.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  h->raw[name] = r;
+  h->den_ready = h->dec_ready = false;
+  return LADIFF_OK;
+}
+
+int ladiff_finalize_weights(ladiff_handle* h, int32_t which, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  h->den_plans.clear();
+  h->dec_plans.clear();
+  if (which & 1) CKS(finalize_denoiser(h, st));
+  if (which & 2) CKS(finalize_decoder(h, st));
+  CK(cudaStreamSynchronize(st));
+  return LADIFF_OK;
+}
+
+int ladiff_diffusion_reverse(ladiff_handle* h, const float* text_emb_dev, const int32_t* lengths_host, int32_t B,
+                             const float* noise_dev, int32_t n_steps, const int32_t* timesteps_host, const float* c1_host,
+                             const float* c2_host, float guidance_scale, int32_t mode, float* z_out_dev, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  if (!h->den_ready) return h->err.set(LADIFF_ERR_STATE, "denoiser weights not finalised");
+  CKS(check_mode(h, mode));
+  if (!text_emb_dev || !lengths_host || !noise_dev || !timesteps_host || !c1_host || !c2_host || !z_out_dev || B < 1 || n_steps < 1)
+    return h->err.set(LADIFF_ERR_INVALID, "ladiff_diffusion_reverse: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = h->cfg.max_it, S = 2 * B;
+  uint32_t gbits;
+  memcpy(&gbits, &guidance_scale, 4);
+  char key[96];
+  snprintf(key, sizeof(key), "cfg:%d:%d:%d:%08x", B, n_steps, mode, gbits);
+  auto& slot = h->den_plans[key];
+  if (!slot) {
+    slot.reset(new DenoisePlan());
+    int s = build_denoise_plan(h, slot.get(), S, n_steps, mode, true);
+    if (s != LADIFF_OK) {
+      h->den_plans.erase(key);
+      return s;
+    }
+  }
+  DenoisePlan* p = slot.get();
+  // ---- per-call meta (ragged row layout lives on the device)
+  std::vector<int> cnt(S);
+  for (int b = 0; b < B; ++b) {
+    if (lengths_host[b] < 1) return h->err.set(LADIFF_ERR_INVALID, "lengths[%d] = %d", b, lengths_host[b]);
+    int m = (lengths_host[b] + h->cfg.frame_per_latent - 1) / h->cfg.frame_per_latent;
+    cnt[b] = cnt[b + B] = m < T ? m : T;
+  }
+  CKS(enqueue_meta(h, st, cnt.data(), S, p->cnt, p->off, p->R, p->row_seq, p->row_t, nullptr, 0));
+  CK(cudaMemcpyAsync(p->text768, text_emb_dev, static_cast<size_t>(S) * 768 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(p->lat, noise_dev, static_cast<size_t>(B) * T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // ---- schedule-dependent tables (cached)
+  std::vector<int> ts(timesteps_host, timesteps_host + n_steps);
+  std::vector<float> coef(2 * n_steps);
+  for (int i = 0; i < n_steps; ++i) {
+    coef[2 * i] = c1_host[i];
+    coef[2 * i + 1] = c2_host[i];
+  }
+  if (ts != p->cached_ts || coef != p->cached_coef) {
+    CK(cudaStreamSynchronize(st));  // previous users of the tables
+    CK(cudaMemcpyAsync(p->ts, ts.data(), n_steps * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->coef, coef.data(), 2 * n_steps * sizeof(float), cudaMemcpyHostToDevice, st));
+    CKS(enqueue_time_tables(h, p, st));
+    CK(cudaStreamSynchronize(st));
+    p->cached_ts = ts;
+    p->cached_coef = coef;
+  }
+  CKS(run_graphed(h, st, &p->exec, &p->graph_launches, [&](cudaStream_t s) { return enqueue_reverse_body(h, p, s, guidance_scale); }));
+  LAUNCH(k_z_out, cdiv(static_cast<long>(B) * T * 256, 256), 256, 0, st, p->lat, p->off, B, T, z_out_dev);
+  return LADIFF_OK;
+}
+
+int ladiff_denoiser_forward(ladiff_handle* h, const float* sample_dev, int32_t timestep, const float* text_emb_dev,
+                            const int32_t* max_iter_elements_host, int32_t S, int32_t mode, float* out_dev, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  if (!h->den_ready) return h->err.set(LADIFF_ERR_STATE, "denoiser weights not finalised");
+  CKS(check_mode(h, mode));
+  if (!sample_dev || !text_emb_dev || !max_iter_elements_host || !out_dev || S < 1)
+    return h->err.set(LADIFF_ERR_INVALID, "ladiff_denoiser_forward: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = h->cfg.max_it;
+  char key[96];
+  snprintf(key, sizeof(key), "fwd:%d:%d", S, mode);
+  auto& slot = h->den_plans[key];
+  if (!slot) {
+    slot.reset(new DenoisePlan());
+    int s = build_denoise_plan(h, slot.get(), S, 1, mode, false);
+    if (s != LADIFF_OK) {
+      h->den_plans.erase(key);
+      return s;
+    }
+  }
+  DenoisePlan* p = slot.get();
+  std::vector<int> cnt(S);
+  for (int s = 0; s < S; ++s) {
+    if (max_iter_elements_host[s] < 1) return h->err.set(LADIFF_ERR_INVALID, "max_iter_elements[%d] = %d", s, max_iter_elements_host[s]);
+    cnt[s] = max_iter_elements_host[s] < T ? max_iter_elements_host[s] : T;
+  }
+  CKS(enqueue_meta(h, st, cnt.data(), S, p->cnt, p->off, p->R, p->row_seq, p->row_t, nullptr, 0));
+  CK(cudaMemcpyAsync(p->text768, text_emb_dev, static_cast<size_t>(S) * 768 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(p->ts, &timestep, sizeof(int), cudaMemcpyHostToDevice, st));
+  CKS(enqueue_time_tables(h, p, st));
+  CKS(enqueue_text_tables(h, p, st));
+  LAUNCH(k_pack_x, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, sample_dev, S, T, h->den_pe, p->row_seq, p->row_t, p->R,
+         p->xin.act, p->planes);
+  CKS(enqueue_den_tokens(h, p, st, 0));
+  LAUNCH(k_final_ln_out, cdiv(static_cast<long>(S) * T * 32, 256), 256, 0, st, p->xa.act.f32, p->off, S, T, h->den_fg, h->den_fb, out_dev);
+  return LADIFF_OK;
+}
+
+int ladiff_cfg_ddim_step(ladiff_handle* h, const float* noise_pred_dev, float* latents_dev, int32_t B, float guidance_scale,
+                         float c1, float c2, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  if (!noise_pred_dev || !latents_dev || B < 1) return h->err.set(LADIFF_ERR_INVALID, "ladiff_cfg_ddim_step: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long n_half = static_cast<long>(B) * h->cfg.max_it * 256;
+  LAUNCH(k_cfg_ddim_dense, cdiv(n_half / 4, 256), 256, 0, st, noise_pred_dev, latents_dev, n_half, guidance_scale, c1, c2);
+  return LADIFF_OK;
+}
+
+int ladiff_vae_decode(ladiff_handle* h, const float* z_dev, const int32_t* lengths_host, int32_t B, int32_t max_len,
+                      int32_t mode, float* out_dev, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  if (!h->dec_ready) return h->err.set(LADIFF_ERR_STATE, "vae decoder weights not finalised");
+  CKS(check_mode(h, mode));
+  if (!z_dev || !lengths_host || !out_dev || B < 1) return h->err.set(LADIFF_ERR_INVALID, "ladiff_vae_decode: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = h->cfg.max_it, nf = h->cfg.nfeats;
+  std::vector<int> cnt(B), mcnt(B);
+  for (int b = 0; b < B; ++b) {
+    const int L = lengths_host[b];
+    if (L < 1 || L > h->cfg.max_frames || L > max_len)
+      return h->err.set(LADIFF_ERR_INVALID, "lengths[%d] = %d outside [1, min(max_frames=%d, max_len=%d)]", b, L, h->cfg.max_frames, max_len);
+    cnt[b] = L;
+    int m = (L + h->cfg.frame_per_latent - 1) / h->cfg.frame_per_latent;
+    mcnt[b] = m < T ? m : T;
+  }
+  char key[96];
+  snprintf(key, sizeof(key), "dec:%d:%d", B, mode);
+  auto& slot = h->dec_plans[key];
+  if (!slot) {
+    slot.reset(new DecodePlan());
+    int s = build_decode_plan(h, slot.get(), B, mode);
+    if (s != LADIFF_OK) {
+      h->dec_plans.erase(key);
+      return s;
+    }
+  }
+  DecodePlan* p = slot.get();
+  CKS(enqueue_meta(h, st, cnt.data(), B, p->cnt, p->foff, p->Rf, p->frow_seq, p->frow_t, p->frow_dst, max_len));
+  CKS(enqueue_meta(h, st, mcnt.data(), B, p->mcnt, p->moff, p->Rm, p->mrow_seq, p->mrow_t, nullptr, 0));
+  CK(cudaMemcpyAsync(p->z, z_dev, static_cast<size_t>(T) * B * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(B) * max_len * nf * sizeof(float), st));  // padded frames: exact zeros
+  CKS(run_graphed(h, st, &p->exec, &p->graph_launches, [&](cudaStream_t s) { return enqueue_decode_body(h, p, s); }));
+  // final_layer (256 -> nfeats) scattering rows straight into [B, max_len, nfeats]; outside the graph: per-call pointer
+  LinCall c;
+  c.A = &p->xn; c.W = &h->dec_final; c.M_max = p->Rmax; c.M_dev = p->Rf; c.row_map = p->frow_dst;
+  c.out = f32_only(out_dev, nf);
+  CKS(launch_linear(h, st, mode, c));
+  return LADIFF_OK;
+}
+
+int ladiff_feats2joints(ladiff_handle* h, const float* feats_dev, const float* mean_dev, const float* std_dev, int32_t B,
+                        int32_t max_len, int32_t njoints, float* joints_dev, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  if (!feats_dev || !mean_dev || !std_dev || !joints_dev || B < 1 || max_len < 1 || max_len > SA_MAXL || njoints < 2 ||
+      (njoints - 1) * 3 + 4 > h->cfg.nfeats)
+    return h->err.set(LADIFF_ERR_INVALID, "ladiff_feats2joints: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(k_feats2joints, B, 256, 0, st, feats_dev, mean_dev, std_dev, max_len, h->cfg.nfeats, njoints, joints_dev);
+  return LADIFF_OK;
+}
+
+int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const float* W_dev, const float* bias_dev, const float* res_dev,
+                       const float* ln_g_dev, const float* ln_b_dev, const float* mod_dev, int32_t M, int32_t N, int32_t K,
+                       int32_t epilogue, int32_t mode, float* out_dev, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  CKS(check_mode(h, mode));
+  if (!A_dev || !W_dev || !out_dev || M < 1 || N < 1 || K < 64 || K % 64) return h->err.set(LADIFF_ERR_INVALID, "ladiff_linear_test: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ar;
+  Weight w;
+  CKS(pack_weight(h, ar, st, &w, W_dev, K, N, K, bias_dev));
+  const int planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
+  ActBuf a;
+  CKS(alloc_act(h, ar, &a, M, K, true, planes > 0));
+  LAUNCH(k_unary, cdiv(static_cast<long>(M) * K, 256), 256, 0, st, A_dev, K, M, K, (int)U_COPY, a.act, planes);
+  LinCall c;
+  c.A = &a; c.W = &w; c.M_max = M; c.epi = epilogue; c.res = res_dev; c.ldres = N; c.ln_g = ln_g_dev; c.ln_b = ln_b_dev; c.mod = mod_dev;
+  c.out = f32_only(out_dev, N);
+  CKS(launch_linear(h, st, mode, c));
+  CK(cudaStreamSynchronize(st));
+  return LADIFF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+"""The fused linear (both backends, every epilogue) against a plain torch fp32 reference of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# tolerance = max-abs error / max-abs reference
+TOL = {"fp32": 2e-6, "bf16x3": 4e-5, "bf16": 2e-2}
+
+
+def ref_linear(A, W, bias, res, g, b, mod, epi):
+    y = F.linear(A.double(), W.double(), bias.double())
+    if epi == "relu":
+        y = F.relu(y)
+    elif epi == "gelu":
+        y = F.gelu(y)
+    elif epi == "silu":
+        y = F.silu(y)
+    elif epi == "res":
+        y = y + res.double()
+    elif epi == "ln":
+        y = F.layer_norm(y + res.double(), (256,), g.double(), b.double(), 1e-5)
+    elif epi == "ln_mod_silu":
+        y = F.layer_norm(y, (256,), g.double(), b.double(), 1e-5)
+        y = F.silu(y * (1 + mod[:256].double()) + mod[256:].double())
+    return y
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("shape,epi", [
+    ((200, 256, 256), "bias"), ((1280, 1024, 256), "relu"), ((1280, 1024, 256), "gelu"), ((130, 768, 1024), "bias"),
+    ((1280, 256, 1024), "ln"), ((77, 256, 256), "ln"), ((640, 256, 1024), "ln_mod_silu"), ((640, 256, 256), "res"),
+    ((50, 256, 768), "silu"), ((300, 263, 256), "bias"), ((5000, 768, 256), "bias"), ((4100, 256, 512), "ln"),
+    ((1, 256, 256), "bias"), ((129, 4608, 256), "bias"),
+])
+def test_linear(engine, mode, shape, epi):
+    from ladiff_b200._lib import MODES
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((M, K), generator=g).cuda()
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).cuda()
+    bias = (0.1 * torch.randn((N,), generator=g)).cuda()
+    res = torch.randn((M, N), generator=g).cuda()
+    lg = (1 + 0.1 * torch.randn((256,), generator=g)).cuda()
+    lb = (0.1 * torch.randn((256,), generator=g)).cuda()
+    mod = (0.3 * torch.randn((512,), generator=g)).cuda()
+    out = engine.linear_test(A, W, bias, res, lg, lb, mod, epilogue=epi, mode=MODES[mode])
+    ref = ref_linear(A, W, bias, res, lg, lb, mod, epi)
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err < TOL[mode], f"{mode} {shape} {epi}: rel max err {err:.3e}"

@@ -1,0 +1,157 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's own outputs (tests/golden, produced by the
+unmodified reference modules) and with the CPU oracle on seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ladiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# max-abs tolerance on decoded features (north_star: 1e-3 on the fp32-accumulate paths; bf16 measured)
+FEATS_TOL = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 0.25}
+
+
+def ddim_tables(n):
+    acp = O.ddim_alphas_cumprod().double()
+    ts = O.ddim_timesteps(n)
+    c1, c2 = [], []
+    for t in ts:
+        p = int(t) - 1000 // n
+        a_t = acp[int(t)]
+        a_p = acp[p] if p >= 0 else acp[0]
+        c1.append(float((a_p / a_t).sqrt()))
+        c2.append(float((1 - a_p).sqrt() - a_p.sqrt() * (1 - a_t).sqrt() / a_t.sqrt()))
+    return [int(t) for t in ts], c1, c2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+def test_denoiser_forward_vs_reference(engine, golden_dir, mode):
+    from ladiff_b200._lib import MODES
+    G = np.load(os.path.join(golden_dir, "denoiser_step.npz"))
+    lengths = G["lengths"].tolist()
+    B = len(lengths)
+    g = torch.Generator().manual_seed(int(G["input_seed"]))
+    text = torch.randn((2 * B, 1, 768), generator=g)
+    x = O.initial_latents(torch.randn((B, 5, 256), generator=g), lengths)
+    mie = O.max_iter_elements_of(lengths).tolist() * 2
+    out = engine.denoiser_forward(torch.cat([x] * 2).cuda(), int(G["timestep"]), text.cuda(), mie, MODES[mode]).cpu()
+    ref = torch.from_numpy(G["out"])
+    valid = O.latent_mask_of(torch.tensor(mie))
+    err = (out - ref)[valid].abs().max().item()
+    assert (out[~valid] == 0).all()
+    tol = {"fp32": 5e-5, "bf16x3": 2e-4, "bf16": 0.1}[mode]
+    assert err < tol, f"{mode}: denoiser.forward max-abs err {err:.3e} (ref scale {ref.abs().max():.2f})"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+def test_sampling_vs_reference(engine, golden_dir, mode):
+    from ladiff_b200._lib import MODES
+    G = np.load(os.path.join(golden_dir, "sampling.npz"))
+    lengths = G["lengths"].tolist()
+    text, noise, _ = O.synthetic_inputs(len(lengths), seed=int(G["input_seed"]))
+    ts, c1, c2 = ddim_tables(50)
+    z = engine.diffusion_reverse(text.cuda(), lengths, noise.cuda(), ts, c1, c2, 7.5, MODES[mode])
+    feats = engine.vae_decode(z, lengths, MODES[mode]).cpu()
+    z = z.cpu()
+    zref, fref = torch.from_numpy(G["z"]), torch.from_numpy(G["feats"])
+    m = O.max_iter_elements_of(lengths)
+    for b, mb in enumerate(m):
+        assert (z[int(mb):, b] == 0).all(), "masked latent rows must be exact zeros (ladiff.py:562-566)"
+    for b, L in enumerate(lengths):
+        assert (feats[b, L:] == 0).all(), "padded frames must be exact zeros (ladiff_vae.py:358)"
+    zerr, ferr = (z - zref).abs().max().item(), (feats - fref).abs().max().item()
+    print(f"[{mode}] latents max-abs err {zerr:.3e} (scale {zref.abs().max():.1f}); feats max-abs err {ferr:.3e}")
+    assert ferr < FEATS_TOL[mode], f"{mode}: decoded features max-abs err {ferr:.3e}"
+    # 20-step schedule (the shipped YAML default, configs/modules/scheduler.yaml:3)
+    ts, c1, c2 = ddim_tables(20)
+    z20 = engine.diffusion_reverse(text.cuda(), lengths, noise.cuda(), ts, c1, c2, 7.5, MODES[mode]).cpu()
+    e20 = (z20 - torch.from_numpy(G["z20"])).abs().max().item()
+    assert e20 < {"fp32": 5e-3, "bf16x3": 5e-2, "bf16": 50.0}[mode], f"{mode}: 20-step latents err {e20:.3e}"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", ["decode", "decode_kit"])
+def test_decode_vs_reference(engine, golden_dir, oracle_sd, mode, name):
+    from ladiff_b200._lib import MODES, Engine
+    G = np.load(os.path.join(golden_dir, name + ".npz"))
+    lengths = G["lengths"].tolist()
+    fref = torch.from_numpy(G["feats"])
+    nf = fref.shape[-1]
+    eng = engine
+    if nf != 263:
+        sdk = O.make_state_dict(1234, nf, perturb=True)
+        eng = Engine(nfeats=nf)
+        eng.set_weights({k: v.cuda() for k, v in O.sub(sdk, "vae.").items()}, "vae.")
+        eng.finalize(2)
+    g = torch.Generator().manual_seed(int(G["input_seed"]))
+    zin = O.initial_latents(torch.randn((len(lengths), 5, 256), generator=g), lengths).permute(1, 0, 2).contiguous()
+    feats = eng.vae_decode(zin.cuda(), lengths, MODES[mode]).cpu()
+    assert feats.shape == fref.shape
+    for b, L in enumerate(lengths):
+        assert (feats[b, L:] == 0).all()
+    err = (feats - fref).abs().max().item()
+    tol = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 0.25}[mode]
+    print(f"[{mode}] {name}: feats max-abs err {err:.3e}")
+    assert err < tol, f"{mode} {name}: max-abs err {err:.3e}"
+
+
+def test_cfg_ddim_step(engine):
+    g = torch.Generator().manual_seed(3)
+    B = 37
+    pred = torch.randn((2 * B, 5, 256), generator=g)
+    lat = torch.randn((B, 5, 256), generator=g)
+    out = engine.cfg_ddim_step(pred.cuda(), lat.cuda(), 7.5, 1.12285173, -0.12325197).cpu()
+    u, c = pred.chunk(2)
+    eps = u + 7.5 * (c - u)
+    acp = O.ddim_alphas_cumprod()
+    ref = O.ddim_step(eps, 981, lat, acp, 50)
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+def test_feats2joints(engine):
+    g = torch.Generator().manual_seed(5)
+    B, L = 6, 196
+    feats = torch.randn((B, L, 263), generator=g) * 0.5
+    mean, std = torch.randn((263,), generator=g) * 0.1, torch.rand((263,), generator=g) + 0.5
+    out = engine.feats2joints(feats.cuda(), mean.cuda(), std.cuda(), 22).cpu()
+    ref = O.feats2joints(feats, mean, std, 22)
+    err = (out - ref).abs().max().item()
+    assert out.shape == ref.shape and err < 5e-3, f"feats2joints max-abs err {err:.3e} (scale {ref.abs().max():.1f})"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_batch32_ragged_vs_oracle(engine, oracle_sd, mode):
+    """Seeded ragged batch (SURVEY.md 8d lengths), CUDA path vs the CPU oracle run here."""
+    from ladiff_b200._lib import MODES
+    B = 32
+    text, noise, lengths = O.synthetic_inputs(B, seed=1234, ragged=True)
+    ts, c1, c2 = ddim_tables(50)
+    z = engine.diffusion_reverse(text.cuda(), lengths, noise.cuda(), ts, c1, c2, 7.5, MODES[mode])
+    feats = engine.vae_decode(z, lengths, MODES[mode]).cpu()
+    ref = O.sample_motion(oracle_sd, text, lengths, noise)
+    err = (feats - ref).abs().max().item()
+    print(f"[{mode}] B=32 ragged feats max-abs err {err:.3e}")
+    assert err < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_batch128_properties(engine, mode):
+    """Full-size config (B=128, 196 frames): batch-composition independence -- a sample decoded inside the batch
+    equals the same sample run alone (attention never crosses sequences), and repeat runs are bit-identical."""
+    from ladiff_b200._lib import MODES
+    B = 128
+    text, noise, lengths = O.synthetic_inputs(B, seed=99, ragged=False)
+    ts, c1, c2 = ddim_tables(50)
+    z = engine.diffusion_reverse(text.cuda(), lengths, noise.cuda(), ts, c1, c2, 7.5, MODES[mode])
+    f1 = engine.vae_decode(z, lengths, MODES[mode])
+    z2 = engine.diffusion_reverse(text.cuda(), lengths, noise.cuda(), ts, c1, c2, 7.5, MODES[mode])
+    assert torch.equal(z, z2), "graph replay must be deterministic"
+    idx = [0, 77, 127]
+    sub_text = torch.cat([text[idx], text[[B + i for i in idx]]])
+    zs = engine.diffusion_reverse(sub_text.cuda(), [lengths[i] for i in idx], noise[idx].cuda(), ts, c1, c2, 7.5, MODES[mode])
+    fs = engine.vae_decode(zs, [lengths[i] for i in idx], MODES[mode])
+    assert torch.isfinite(f1).all()
+    assert torch.equal(fs, f1[idx]), "a sample's result must not depend on its batch neighbours"
