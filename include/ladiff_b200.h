@@ -133,6 +133,11 @@ LADIFF_API int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const fl
                        const float* res_dev, const float* ln_g_dev, const float* ln_b_dev, const float* mod_dev,
                        int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t mode, float* out_dev, void* stream);
 
+/* Measurement hook: average device time (CUDA events on `stream`) of `iters` launches of one fused linear of the given
+ * shape / epilogue / mode on pseudo-random operands -- the same kernel instances the plans launch. */
+LADIFF_API int ladiff_linear_bench(ladiff_handle* h, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t mode,
+                        int32_t iters, float* ms_per_launch_host, void* stream);
+
 /* Number of kernel launches (graph nodes included) enqueued by the last compute call on this handle. */
 LADIFF_API int64_t ladiff_last_launch_count(const ladiff_handle* h);
 

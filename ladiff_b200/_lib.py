@@ -53,11 +53,12 @@ def load_library() -> C.CDLL:
     lib.ladiff_vae_decode.argtypes = [vp, vp, pi32, i32, i32, i32, vp, vp]
     lib.ladiff_feats2joints.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.ladiff_linear_test.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.ladiff_linear_bench.argtypes = [vp, i32, i32, i32, i32, i32, i32, pf32, vp]
     lib.ladiff_last_launch_count.argtypes = [vp]
     lib.ladiff_last_launch_count.restype = i64
     for fn in ("ladiff_create", "ladiff_set_weight", "ladiff_finalize_weights", "ladiff_diffusion_reverse",
                "ladiff_denoiser_forward", "ladiff_cfg_ddim_step", "ladiff_vae_decode", "ladiff_feats2joints",
-               "ladiff_linear_test"):
+               "ladiff_linear_test", "ladiff_linear_bench"):
         getattr(lib, fn).restype = C.c_int
     _lib = lib
     return lib
@@ -65,7 +66,7 @@ def load_library() -> C.CDLL:
 
 EXPORTS = ("ladiff_abi_version", "ladiff_create", "ladiff_destroy", "ladiff_last_error", "ladiff_set_weight",
            "ladiff_finalize_weights", "ladiff_diffusion_reverse", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step",
-           "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_last_launch_count")
+           "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_last_launch_count")
 
 
 def _i32(xs: Sequence[int]):
@@ -211,3 +212,10 @@ class Engine:
         self._check(self.lib.ladiff_linear_test(self._h, _ptr(A), _ptr(W), *[_ptr(t) for t in opt], M, N, K,
                                                 EPI[epilogue], mode, _ptr(out), _stream()), "linear_test")
         return out
+
+    def linear_bench(self, M: int, N: int, K: int, epilogue: str = "bias", mode: int = MODE_BF16X3, iters: int = 20) -> float:
+        """average milliseconds per launch of one fused linear (device time, CUDA events)"""
+        ms = C.c_float(0.0)
+        self._check(self.lib.ladiff_linear_bench(self._h, M, N, K, EPI[epilogue], mode, iters, C.byref(ms), _stream()),
+                    "linear_bench")
+        return float(ms.value)

@@ -480,6 +480,15 @@ __global__ void k_pack_weight(const float* __restrict__ W, int ldw, int N, int K
   pl[static_cast<long>(n_pad) * K + i] = lo;
 }
 
+// deterministic pseudo-random fill in [-scale, scale] (benchmark operands)
+__global__ void k_fill_pseudo(float* __restrict__ p, long n, float scale, unsigned seed) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned x = static_cast<unsigned>(i) * 2654435761u + seed * 40503u;
+  x ^= x >> 16; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+  p[i] = scale * (static_cast<float>(x & 0xFFFFFF) / 8388608.0f - 1.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // feats2joints: de-normalise + recover_from_ric (data/HumanML3D.py:44-48;
 // data/humanml/scripts/motion_process.py:355-381,415-430; quaternion.py:16-20,54-73).  One CTA per sequence:

@@ -79,8 +79,10 @@ struct ActBuf {
 
 struct Arena {
   std::vector<void*> blocks;
-  ~Arena() {
+  ~Arena() { clear(); }
+  void clear() {
     for (void* p : blocks) cudaFree(p);
+    blocks.clear();
   }
   cudaError_t alloc(void** p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
@@ -110,7 +112,8 @@ struct ladiff_handle {
   int device = 0;
   int64_t launches = 0;
   std::map<std::string, Raw> raw;
-  Arena warena;  // packed weights
+  Arena warena_den, warena_dec;  // packed weights
+  Arena* warena = &warena_den;   // arena the pack_* helpers currently fill
   bool den_ready = false, dec_ready = false;
   // denoiser
   DenLayerW den[NL];
@@ -312,7 +315,7 @@ int pack_linear(H* h, cudaStream_t st, Weight* w, const std::string& prefix, int
   const Raw *W, *b;
   CKS(get_raw(h, prefix + ".weight", {N, K}, &W));
   CKS(get_raw(h, prefix + ".bias", {N}, &b));
-  return pack_weight(h, h->warena, st, w, W->dev, K, N, K, b->dev);
+  return pack_weight(h, *h->warena, st, w, W->dev, K, N, K, b->dev);
 }
 
 int get_vec(H* h, const std::string& name, int n, float** out) {
@@ -334,7 +337,7 @@ int pack_concat(H* h, cudaStream_t st, Weight* w, const std::vector<std::pair<co
                        static_cast<size_t>(rows) * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(tmpB + i * rows, parts[i].second->dev + row0, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
-  int s = pack_weight(h, h->warena, st, w, tmpW, K, N, K, tmpB);
+  int s = pack_weight(h, *h->warena, st, w, tmpW, K, N, K, tmpB);
   CK(cudaStreamSynchronize(st));
   cudaFree(tmpW);
   cudaFree(tmpB);
@@ -343,6 +346,9 @@ int pack_concat(H* h, cudaStream_t st, Weight* w, const std::vector<std::pair<co
 
 int finalize_denoiser(H* h, cudaStream_t st) {
   const int D = 256;
+  h->den_ready = false;
+  h->warena_den.clear();
+  h->warena = &h->warena_den;
   const std::string P = "denoiser.";
   CKS(pack_linear(h, st, &h->time1, P + "time_embedding.linear_1", D, 768));
   CKS(pack_linear(h, st, &h->time2, P + "time_embedding.linear_2", D, D));
@@ -359,7 +365,7 @@ int finalize_denoiser(H* h, cudaStream_t st) {
     const Raw *ipw, *ipb;
     CKS(get_raw(h, L + "sa_block.self_attn.in_proj_weight", {3 * D, D}, &ipw));
     CKS(get_raw(h, L + "sa_block.self_attn.in_proj_bias", {3 * D}, &ipb));
-    CKS(pack_weight(h, h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
+    CKS(pack_weight(h, *h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
     inproj.push_back({ipw, ipb});
     CKS(pack_linear(h, st, &w.out, L + "sa_block.self_attn.out_proj", D, D));
     CKS(pack_linear(h, st, &w.ff1, L + "sa_block.linear1", 1024, D));
@@ -403,6 +409,9 @@ int finalize_denoiser(H* h, cudaStream_t st) {
 
 int finalize_decoder(H* h, cudaStream_t st) {
   const int D = 256;
+  h->dec_ready = false;
+  h->warena_dec.clear();
+  h->warena = &h->warena_dec;
   const std::string P = "vae.";
   const Raw* pe;
   CKS(get_raw(h, P + "query_pos_decoder.pe", {500, 1, D}, &pe));
@@ -416,11 +425,11 @@ int finalize_decoder(H* h, cudaStream_t st) {
     const Raw *ipw, *ipb, *mw, *mb;
     CKS(get_raw(h, L + "self_attn.in_proj_weight", {3 * D, D}, &ipw));
     CKS(get_raw(h, L + "self_attn.in_proj_bias", {3 * D}, &ipb));
-    CKS(pack_weight(h, h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
+    CKS(pack_weight(h, *h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
     CKS(pack_linear(h, st, &w.out, L + "self_attn.out_proj", D, D));
     CKS(get_raw(h, L + "multihead_attn.in_proj_weight", {3 * D, D}, &mw));
     CKS(get_raw(h, L + "multihead_attn.in_proj_bias", {3 * D}, &mb));
-    CKS(pack_weight(h, h->warena, st, &w.q2, mw->dev, D, D, D, mb->dev));
+    CKS(pack_weight(h, *h->warena, st, &w.q2, mw->dev, D, D, D, mb->dev));
     memproj.push_back({mw, mb});
     CKS(pack_linear(h, st, &w.out2, L + "multihead_attn.out_proj", D, D));
     CKS(pack_linear(h, st, &w.ff1, L + "linear1", h->cfg.ff_size, D));
@@ -864,17 +873,24 @@ int ladiff_set_weight(ladiff_handle* h, const char* name, const float* data_dev,
   CK(cudaMalloc(&r.dev, r.numel() * sizeof(float)));
   CK(cudaMemcpyAsync(r.dev, data_dev, r.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st));
   h->raw[name] = r;
-  h->den_ready = h->dec_ready = false;
+  if (strncmp(name, "denoiser.", 9) == 0) h->den_ready = false;
+  else if (strncmp(name, "vae.", 4) == 0) h->dec_ready = false;
+  else h->den_ready = h->dec_ready = false;
   return LADIFF_OK;
 }
 
 int ladiff_finalize_weights(ladiff_handle* h, int32_t which, void* stream) {
   if (!h) return LADIFF_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  h->den_plans.clear();
-  h->dec_plans.clear();
-  if (which & 1) CKS(finalize_denoiser(h, st));
-  if (which & 2) CKS(finalize_decoder(h, st));
+  CK(cudaDeviceSynchronize());  // plans may still be in flight
+  if (which & 1) {
+    h->den_plans.clear();
+    CKS(finalize_denoiser(h, st));
+  }
+  if (which & 2) {
+    h->dec_plans.clear();
+    CKS(finalize_decoder(h, st));
+  }
   CK(cudaStreamSynchronize(st));
   return LADIFF_OK;
 }
@@ -1060,6 +1076,50 @@ int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const float* W_dev,
   c.out = f32_only(out_dev, N);
   CKS(launch_linear(h, st, mode, c));
   CK(cudaStreamSynchronize(st));
+  return LADIFF_OK;
+}
+
+// Times `iters` back-to-back launches of one fused linear (same kernels as the plans) with CUDA events on `stream`.
+int ladiff_linear_bench(ladiff_handle* h, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t mode, int32_t iters,
+                        float* ms_per_launch_host, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  CKS(check_mode(h, mode));
+  if (!ms_per_launch_host || M < 1 || N < 1 || K < 64 || K % 64 || iters < 1) return h->err.set(LADIFF_ERR_INVALID, "ladiff_linear_bench: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ar;
+  float *Wsrc = nullptr, *Asrc = nullptr, *vec = nullptr, *res = nullptr;
+  CK(ar.alloc((void**)&Wsrc, static_cast<size_t>(N) * K * sizeof(float)));
+  CK(ar.alloc((void**)&Asrc, static_cast<size_t>(M) * K * sizeof(float)));
+  CK(ar.alloc((void**)&vec, 1024 * sizeof(float)));
+  CK(ar.alloc((void**)&res, static_cast<size_t>(M) * N * sizeof(float)));
+  LAUNCH(k_fill_pseudo, cdiv(static_cast<long>(N) * K, 256), 256, 0, st, Wsrc, static_cast<long>(N) * K, 0.05f, 1u);
+  LAUNCH(k_fill_pseudo, cdiv(static_cast<long>(M) * K, 256), 256, 0, st, Asrc, static_cast<long>(M) * K, 1.0f, 2u);
+  LAUNCH(k_fill_pseudo, 4, 256, 0, st, vec, 1024L, 0.1f, 3u);
+  LAUNCH(k_fill_pseudo, cdiv(static_cast<long>(M) * N, 256), 256, 0, st, res, static_cast<long>(M) * N, 1.0f, 4u);
+  Weight w;
+  CKS(pack_weight(h, ar, st, &w, Wsrc, K, N, K, vec));
+  const int planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
+  ActBuf a, o;
+  CKS(alloc_act(h, ar, &a, M, K, true, planes > 0));
+  CKS(alloc_act(h, ar, &o, M, N, true, planes > 0));
+  LAUNCH(k_unary, cdiv(static_cast<long>(M) * K, 256), 256, 0, st, Asrc, K, M, K, (int)U_COPY, a.act, planes);
+  LinCall c;
+  c.A = &a; c.W = &w; c.M_max = M; c.epi = epilogue; c.res = res; c.ldres = N; c.ln_g = vec; c.ln_b = vec + 256; c.mod = vec + 512;
+  c.out = o.act; c.out_planes = planes;
+  for (int i = 0; i < 3; ++i) CKS(launch_linear(h, st, mode, c));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) CKS(launch_linear(h, st, mode, c));
+  CK(cudaEventRecord(e1, st));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch_host = ms / iters;
   return LADIFF_OK;
 }
 

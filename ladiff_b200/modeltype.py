@@ -1,0 +1,163 @@
+"""Drop-in for the sampling surface of ``ladiff.models.modeltype.ladiff.LADIFF`` (reference lines 27-571):
+``forward`` (:250-308), ``_diffusion_reverse`` LAD branch (:333-571) and ``gen_from_latent`` (:310-318).
+
+Components are still created through ``instantiate_from_config(cfg.model.*)`` (:87-115) -- the reference's plugin
+boundary -- so swapping the ``target:`` strings (``ladiff_b200.config.retarget``) is the whole integration.  The
+N-step loop is ONE C-ABI call (``ladiff_diffusion_reverse``): CFG-doubled denoiser, CFG combine and the scheduler step
+run on the device inside a captured CUDA graph; nothing returns to the host between steps.
+
+Training, losses, metrics and the Lightning hooks are outside the hot path.
+"""
+from __future__ import annotations
+
+import inspect
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from .config import instantiate_from_config
+from .utils import max_iter_elements, remove_padding
+
+
+class LADIFF(nn.Module):
+
+    def __init__(self, cfg, datamodule, **kwargs):
+        super().__init__()
+        self.cfg = cfg
+        self.stage = cfg.TRAIN.STAGE
+        self.condition = cfg.model.condition
+        self.is_vae = cfg.model.vae
+        self.nfeats = cfg.DATASET.NFEATS
+        self.njoints = cfg.DATASET.NJOINTS
+        self.latent_dim = cfg.model.latent_dim
+        self.guidance_scale = cfg.model.guidance_scale
+        self.guidance_uncodp = cfg.model.guidance_uncondp
+        self.datamodule = datamodule
+        abl = cfg.TRAIN.ABLATION
+        self.test_efficiency = abl.get("TEST_EFFICIENCY", False)
+        self.max_it = abl.MAX_IT
+        self.frame_per_latent = abl.FRAME_PER_LATENT
+        self.joint_distro_fix = abl.get("JOINT_DISTRO_FIX", False)
+        self.ARDIFF = cfg.get("ARDIFF", False)
+        self.LAD = abl.get("LAD", True)
+        if cfg.get("IDEA", "ard") != "ard" or self.ARDIFF or not self.LAD or self.joint_distro_fix or self.test_efficiency:
+            raise NotImplementedError("ladiff_b200 implements the LADiff sampling configuration: IDEA 'ard', ARDIFF False, "
+                                      "LAD True, JOINT_DISTRO_FIX False, TEST_EFFICIENCY False "
+                                      "(configs/config_ladiff_humanml3d.yaml:18-19,58-64)")
+        if self.condition not in ("text", "text_uncond"):
+            raise NotImplementedError("text-conditioned sampling only")
+        try:
+            self.vae_type = cfg.model.vae_type
+        except (AttributeError, KeyError):
+            self.vae_type = cfg.model.motion_vae.target.split(".")[-1].lower().replace("vae", "")
+
+        self.text_encoder = instantiate_from_config(cfg.model.text_encoder)
+        self.vae = instantiate_from_config(cfg.model.motion_vae)
+        self.denoiser = instantiate_from_config(cfg.model.denoiser)
+        self.scheduler = instantiate_from_config(cfg.model.scheduler)
+        self.noise_scheduler = instantiate_from_config(cfg.model.noise_scheduler)
+        for p in self.parameters():
+            p.requires_grad = False
+        self.do_classifier_free_guidance = self.guidance_scale > 1.0
+        self.feats2joints = datamodule.feats2joints
+        self._shared_engine = None
+        self.times: List[float] = []
+
+    # -- engine plumbing ------------------------------------------------------------------------------------
+    def _bind(self):
+        """denoiser + VAE (+ feats2joints) share one library handle: one workspace, one stream of work."""
+        if self._shared_engine is None:
+            from ._lib import Engine
+            self._shared_engine = Engine(nfeats=self.nfeats, max_it=self.max_it, frame_per_latent=self.frame_per_latent)
+            self.denoiser.bind_engine(self._shared_engine)
+            self.vae.bind_engine(self._shared_engine)
+            if hasattr(self.datamodule, "bind_engine"):
+                self.datamodule.bind_engine(self._shared_engine)
+        return self._shared_engine
+
+    def set_precision(self, precision: str):
+        """'bf16x3' (default, fp32-grade), 'bf16' (fastest) or 'fp32' (SIMT)."""
+        from ._lib import MODES
+        if precision not in MODES:
+            raise ValueError(f"precision must be one of {sorted(MODES)}")
+        self.denoiser.precision = precision
+        self.vae.precision = precision
+
+    # -- reference API ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, batch, latentwise_gen=None, plot_att_map=None):
+        """batch {"text": List[str], "length": List[int]} -> List[Tensor[L_i, njoints, 3]]  (reference :250-308)."""
+        if latentwise_gen is not None or plot_att_map is not None:
+            raise NotImplementedError("latentwise_gen / plot_att_map are analysis options outside the sampling path")
+        texts = batch["text"]
+        lengths = batch["length"]
+        if self.stage not in ("diffusion", "vae_diffusion"):
+            raise NotImplementedError("stage 'vae' reconstructs from a given motion; not the sampling path")
+        if self.do_classifier_free_guidance:
+            uncond_tokens = [""] * len(texts)           # uncond FIRST (reference :258-264)
+            if self.condition == "text":
+                uncond_tokens.extend(texts)
+            elif self.condition == "text_uncond":
+                uncond_tokens.extend(uncond_tokens)
+            texts = uncond_tokens
+        text_emb = self.text_encoder(texts)
+        z = self._diffusion_reverse(text_emb, lengths)
+        feats_rst = self.vae.decode(z, lengths)
+        return self._to_joints(feats_rst, lengths)
+
+    def _to_joints(self, feats_rst, lengths):
+        if getattr(self.datamodule, "accepts_cuda", False):
+            joints = self.feats2joints(feats_rst.detach()).cpu()      # de-normalise + recover_from_ric on the GPU
+        else:
+            joints = self.feats2joints(feats_rst.detach().cpu())      # reference behaviour (:307)
+        return remove_padding(joints, lengths)
+
+    @torch.no_grad()
+    def gen_from_latent(self, batch):
+        """reference :310-318"""
+        self._bind()
+        feats_rst = self.vae.decode(batch["latent"], batch["length"])
+        return self._to_joints(feats_rst, batch["length"])
+
+    @torch.no_grad()
+    def _diffusion_reverse(self, encoder_hidden_states, lengths=None, latents: Optional[torch.Tensor] = None,
+                           generator: Optional[torch.Generator] = None):
+        """encoder_hidden_states [2B,1,768] (uncond rows first), lengths List[int] -> latents [MAX_IT, B, 256] with rows
+        >= ceil(L/48) exactly zero (reference :333-571, LAD branch).  ``latents=`` / ``generator=`` inject the initial noise
+        the reference draws from the global RNG (:380-385)."""
+        if lengths is None:
+            raise ValueError("lengths are required on the length-aware path")
+        engine = self._bind()
+        bsz = encoder_hidden_states.shape[0]
+        guidance = float(self.guidance_scale)
+        if self.do_classifier_free_guidance:
+            bsz = bsz // 2
+        else:   # no guidance: eps = denoiser(cond); expressed as the CFG kernel with both halves equal and g = 1
+            encoder_hidden_states = torch.cat([encoder_hidden_states] * 2)
+            guidance = 1.0
+        if len(lengths) != bsz:
+            raise ValueError(f"{len(lengths)} lengths for {bsz} prompts")
+        if latents is None:
+            latents = torch.randn((bsz, self.max_it, self.latent_dim[-1]), device=encoder_hidden_states.device,
+                                  dtype=torch.float, generator=generator)
+        latents = latents * self.scheduler.init_noise_sigma                     # :407 (masked rows are never read)
+        self.scheduler.set_timesteps(self.cfg.model.scheduler.num_inference_timesteps)   # :410
+        eta = 0.0
+        if "eta" in set(inspect.signature(self.scheduler.step).parameters.keys()):       # :415-417
+            eta = self.cfg.model.scheduler.get("eta", 0.0)
+        if not hasattr(self.scheduler, "fused_coefficients"):
+            raise NotImplementedError("the fused loop needs a scheduler exposing fused_coefficients() (DDIM, eta=0)")
+        ts, c1, c2 = self.scheduler.fused_coefficients(eta)
+        self.denoiser.engine()       # weight sync
+        return engine.diffusion_reverse(encoder_hidden_states, [int(x) for x in lengths], latents, ts, c1, c2,
+                                        guidance, self.denoiser.mode)
+
+    @torch.no_grad()
+    def sample_features(self, encoder_hidden_states, lengths, latents=None, generator=None):
+        """_diffusion_reverse + vae.decode without leaving the device: [B, max(lengths), nfeats] CUDA tensor."""
+        z = self._diffusion_reverse(encoder_hidden_states, lengths, latents=latents, generator=generator)
+        return self.vae.decode(z, lengths)
+
+    def t2m_eval(self, batch):
+        raise NotImplementedError("t2m_eval needs the pretrained T2M evaluators and datasets (SURVEY.md 8f row 3)")
