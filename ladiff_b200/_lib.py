@@ -101,6 +101,8 @@ class Engine:
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("ladiff_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if os.environ.get("LADIFF_NO_GRAPH"):      # profiling / debugging: launch kernel by kernel
+            use_cuda_graph = False
         self.cfg = LadiffConfig(nfeats, num_layers, latent_dim, num_heads, ff_size, text_dim, max_it, frame_per_latent,
                                 max_frames, 1 if use_cuda_graph else 0)
         self.nfeats, self.max_it, self.max_frames = nfeats, max_it, max_frames

@@ -68,7 +68,7 @@ struct Weight {
   float* Wt = nullptr;
   __nv_bfloat16* pl = nullptr;
   float* bias = nullptr;
-  CUtensorMap map;
+  CUtensorMap map64, map128, map256;  // TMA boxes of 64 / 128 / 256 weight rows (one load per plane and k-block)
 };
 
 struct ActBuf {
@@ -191,16 +191,54 @@ struct LinCall {
   Act out{nullptr, nullptr, 0, 0};
   int out_planes = 0;
   int n_store = -1;
+  long long* dbg = nullptr;
 };
 
-template <int BN, int NS>
-int launch_tc(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int tiles_m) {
+template <int BN, int NS, int EPI>
+int launch_tc_e(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int tiles_m) {
   using Cfg = TcCfg<BN, NS>;
   dim3 grid(tiles_m, (c.W->N + BN - 1) / BN);
-  k_linear_tc<BN, NS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(c.A->map, c.A2 ? c.A2->map : c.A->map, c.W->map, a);
+  k_linear_tc<BN, NS, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(c.A->map, c.A2 ? c.A2->map : c.A->map,
+                                                                         BN == 64 ? c.W->map64 : (BN == 128 ? c.W->map128 : c.W->map256), a);
   CK(cudaGetLastError());
   h->launches++;
   return LADIFF_OK;
+}
+
+constexpr int LN_CL = 4;  // CTAs per cluster (along N) for the LayerNorm-epilogue linears
+
+template <int NS, int EPI>
+int launch_tc_ln(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int tiles_m) {
+  using Cfg = TcCfg<256 / LN_CL, NS>;
+  dim3 grid(tiles_m, LN_CL);
+  k_linear_tc_ln<LN_CL, NS, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(c.A->map, c.A2 ? c.A2->map : c.A->map,
+                                                                              LN_CL == 4 ? c.W->map64 : c.W->map128, a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return LADIFF_OK;
+}
+
+template <int BN, int NS>
+int launch_tc(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int tiles_m) {
+  switch (c.epi) {
+    case EPI_BIAS: return launch_tc_e<BN, NS, EPI_BIAS>(h, st, c, a, tiles_m);
+    case EPI_RELU: return launch_tc_e<BN, NS, EPI_RELU>(h, st, c, a, tiles_m);
+    case EPI_GELU: return launch_tc_e<BN, NS, EPI_GELU>(h, st, c, a, tiles_m);
+    case EPI_RES: return launch_tc_e<BN, NS, EPI_RES>(h, st, c, a, tiles_m);
+    case EPI_SILU: return launch_tc_e<BN, NS, EPI_SILU>(h, st, c, a, tiles_m);
+    case EPI_LN:
+      if (BN == 256 && c.out.ld % 8 == 0 && !c.row_map && tiles_m * LN_CL <= 2 * 148 && !getenv("LADIFF_NO_CLUSTER"))
+        return launch_tc_ln<NS, EPI_LN>(h, st, c, a, tiles_m);
+      if (BN == 256) return launch_tc_e<256, NS, EPI_LN>(h, st, c, a, tiles_m);
+      break;
+    case EPI_LN_MOD_SILU:
+      if (BN == 256 && c.out.ld % 8 == 0 && !c.row_map && tiles_m * LN_CL <= 2 * 148 && !getenv("LADIFF_NO_CLUSTER"))
+        return launch_tc_ln<NS, EPI_LN_MOD_SILU>(h, st, c, a, tiles_m);
+      if (BN == 256) return launch_tc_e<256, NS, EPI_LN_MOD_SILU>(h, st, c, a, tiles_m);
+      break;
+    default: break;
+  }
+  return h->err.set(LADIFF_ERR_INVALID, "unsupported epilogue %d for BN %d", c.epi, BN);
 }
 
 int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
@@ -234,6 +272,8 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
   a.out = c.out;
   a.out_planes = c.out_planes;
   a.n_store = c.n_store < 0 ? W.N : c.n_store;
+  a.dbg = c.dbg;
+  a.dbg_flags = getenv("LADIFF_DBG_FLAGS") ? atoi(getenv("LADIFF_DBG_FLAGS")) : 0;
   const bool ln = (c.epi == EPI_LN || c.epi == EPI_LN_MOD_SILU);
   if (ln && W.N != 256) return h->err.set(LADIFF_ERR_INVALID, "LayerNorm epilogue needs N == 256");
   if (c.M_max <= 0) return LADIFF_OK;
@@ -307,7 +347,11 @@ int pack_weight(H* h, Arena& ar, cudaStream_t st, Weight* w, const float* W_dev,
     CK(cudaMemcpyAsync(w->bias, bias_dev, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   LAUNCH(k_pack_weight, cdiv(static_cast<long>(w->n_pad) * K, 256), 256, 0, st, W_dev, ldw, N, K, w->n_pad, w->Wt, w->pl);
-  if (K % 64 == 0) CKS(make_map(h, &w->map, w->pl, 2ull * w->n_pad, K, K, 64));
+  if (K % 64 == 0) {
+    CKS(make_map(h, &w->map64, w->pl, 2ull * w->n_pad, K, K, 64));
+    CKS(make_map(h, &w->map128, w->pl, 2ull * w->n_pad, K, K, 128));
+    CKS(make_map(h, &w->map256, w->pl, 2ull * w->n_pad, K, K, 256));
+  }
   return LADIFF_OK;
 }
 
@@ -779,9 +823,24 @@ int run_graphed(H* h, cudaStream_t st, cudaGraphExec_t* exec, int64_t* graph_lau
   return LADIFF_OK;
 }
 
+template <int BN, int NS, int EPI>
+cudaError_t set_tc_attr_e() {
+  return cudaFuncSetAttribute(k_linear_tc<BN, NS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, NS>::SMEM_BYTES);
+}
 template <int BN, int NS>
 cudaError_t set_tc_attr() {
-  return cudaFuncSetAttribute(k_linear_tc<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, NS>::SMEM_BYTES);
+  cudaError_t e = set_tc_attr_e<BN, NS, EPI_BIAS>();
+  if (e == cudaSuccess) e = set_tc_attr_e<BN, NS, EPI_RELU>();
+  if (e == cudaSuccess) e = set_tc_attr_e<BN, NS, EPI_GELU>();
+  if (e == cudaSuccess) e = set_tc_attr_e<BN, NS, EPI_RES>();
+  if (e == cudaSuccess) e = set_tc_attr_e<BN, NS, EPI_SILU>();
+  if (e == cudaSuccess && BN == 256) e = set_tc_attr_e<256, NS, EPI_LN>();
+  if (e == cudaSuccess && BN == 256) e = set_tc_attr_e<256, NS, EPI_LN_MOD_SILU>();
+  if (e == cudaSuccess && BN == 256)
+    e = cudaFuncSetAttribute(k_linear_tc_ln<LN_CL, NS, EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256 / LN_CL, NS>::SMEM_BYTES);
+  if (e == cudaSuccess && BN == 256)
+    e = cudaFuncSetAttribute(k_linear_tc_ln<LN_CL, NS, EPI_LN_MOD_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256 / LN_CL, NS>::SMEM_BYTES);
+  return e;
 }
 
 int check_mode(H* h, int mode) {
@@ -1120,6 +1179,24 @@ int ladiff_linear_bench(ladiff_handle* h, int32_t M, int32_t N, int32_t K, int32
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *ms_per_launch_host = ms / iters;
+  if (getenv("LADIFF_DBG_STAMPS") && mode != LADIFF_MODE_FP32) {
+    long long* dbg = nullptr;
+    const int ncta = 4096;
+    CK(ar.alloc((void**)&dbg, ncta * 16 * sizeof(long long)));
+    CK(cudaMemsetAsync(dbg, 0, ncta * 16 * sizeof(long long), st));
+    c.dbg = dbg;
+    CKS(launch_linear(h, st, mode, c));
+    CK(cudaStreamSynchronize(st));
+    std::vector<long long> hb(ncta * 16);
+    CK(cudaMemcpy(hb.data(), dbg, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int cta : {0, 9}) {
+      const long long* d = hb.data() + cta * 16;
+      if (!d[0]) continue;
+      fprintf(stderr, "  cta %3d: setup %lld | tma0-issued %lld | tma-all %lld | first-full %lld | last-full %lld | mma-done-issue %lld | accum-ready %lld | epi-done %lld | e10 %lld e11 %lld e12 %lld e13 %lld\n",
+              cta, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - d[0], d[7] - d[0], d[8] - d[0],
+              d[10] - d[0], d[11] - d[0], d[12] - d[0], d[13] - d[0]);
+    }
+  }
   return LADIFF_OK;
 }
 

@@ -41,10 +41,22 @@ struct LinArgs {
   int n_store;          // columns actually stored (<= N; 263 of 264..)
   // tensor-core backend
   int a_plane_rows, a2_plane_rows, w_plane_rows;  // row offset of the lo plane inside each tensor map
+  int dbg_flags;        // experiments (profiling only)
+  long long* dbg;       // optional per-CTA clock stamps [ncta][16] (profiling builds of ladiff_linear_bench)
 };
 
 // ------------------------------------------------------------------------------------------------
 // scalar epilogue shared by both backends (non-LN kinds)
+template <int EPI>
+__device__ __forceinline__ float epi_pointwise_t(const LinArgs& p, float acc, long row, int col) {
+  float x = acc + (p.bias ? __ldg(p.bias + col) : 0.f);
+  if (EPI == EPI_RELU) x = fmaxf(x, 0.f);
+  else if (EPI == EPI_GELU) x = gelu_erf(x);
+  else if (EPI == EPI_SILU) x = silu(x);
+  else if (EPI == EPI_RES) x += p.res[row * p.ldres + col];
+  return x;
+}
+
 __device__ __forceinline__ float epi_pointwise(const LinArgs& p, float acc, long row, int col) {
   float x = acc + (p.bias ? __ldg(p.bias + col) : 0.f);
   switch (p.epi) {
@@ -151,6 +163,9 @@ __global__ void __launch_bounds__(256) k_linear_simt(const LinArgs p) {
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 backend
+//
+// Shared memory:  [ STAGES x { A planes | W planes } ]  [ per-column vectors 5 KB ]  [ mbarriers ]
+// After the last MMA retires the stage memory is dead, so the epilogue aliases its transposition tiles onto it.
 template <int BN, int NSPLIT>
 struct TcCfg {
   static constexpr int BM = 128, BK = 64, UMMA_K = 16;
@@ -159,53 +174,100 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + W_BYTES);
   static constexpr int STAGES_FIT = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int VEC_OFF = STAGES * STAGE_BYTES;
+  static constexpr int VEC_BYTES = 1280 * 4;  // bias[256] | ln_g[256] | ln_b[256] | scale[256] | shift[256]
+  static constexpr int BAR_OFF = VEC_OFF + VEC_BYTES;
+  static constexpr int STAT_BYTES = 4096;                    // cluster LayerNorm statistics (k_linear_tc_ln)
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + STAT_BYTES + 1024 /*align slack*/;
   static constexpr int THREADS = 192;
+  static constexpr int TILE_LD = 36;                         // floats; 144 B rows keep float4 accesses conflict-free
+  static constexpr int TILE_BYTES = 32 * TILE_LD * 4;        // one warp-private 32x32 fp32 tile
+  static_assert(8 * TILE_BYTES <= STAGES * STAGE_BYTES, "epilogue tiles must fit in the dead stage memory");
 };
 
-__device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* h) {
-  uint4 u;
-  u.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
-  u.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[3])) << 16) | __bfloat16_as_ushort(h[2]);
-  u.z = (static_cast<uint32_t>(__bfloat16_as_ushort(h[5])) << 16) | __bfloat16_as_ushort(h[4]);
-  u.w = (static_cast<uint32_t>(__bfloat16_as_ushort(h[7])) << 16) | __bfloat16_as_ushort(h[6]);
-  return u;
+__device__ __forceinline__ uint32_t pack2_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16) | __bfloat16_as_ushort(a);
 }
 
-// store 32 consecutive finished values of one row (columns col0..col0+31)
-__device__ __forceinline__ void tc_store32(const LinArgs& p, long drow, int col0, const float (&y)[32]) {
-  const bool vec = (p.row_map == nullptr) && (col0 + 32 <= p.n_store) && ((p.out.ld & 7) == 0);
-  if (vec) {
-    if (p.out.f32) {
-      float4* d = reinterpret_cast<float4*>(p.out.f32 + drow * p.out.ld + col0);
+// slow path: per-thread scalar stores (scatter / unaligned / partial column chunk)
+__device__ __forceinline__ void tc_store32_slow(const LinArgs& p, long drow, int col0, const float (&y)[32]) {
+  for (int j = 0; j < 32; ++j)
+    if (col0 + j < p.n_store) act_store(p.out, p.out_planes, drow, col0 + j, y[j]);
+}
+
+// Warp-cooperative, coalesced load of a [32 rows x 32 cols] fp32 block into the warp-private tile, then every thread
+// picks up its own row.  Rows row_base .. row_base+nvalid-1 of `base` (row stride ld) are read, the rest is zero.
+// When `idx` is given the source row of local row rr is idx[row_base + rr] (broadcast add of per-sequence vectors).
+__device__ __forceinline__ void warp_load_rows(float (*tile)[36], const float* __restrict__ base, long ld,
+                                               const int* __restrict__ idx, long row_base, int nvalid, int col0, int lane,
+                                               float (&v)[32]) {
+  float4 a[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr < nvalid) {
+      const long sr = idx ? static_cast<long>(__ldg(idx + row_base + rr)) : row_base + rr;
+      a[i] = *reinterpret_cast<const float4*>(base + sr * ld + col0 + (lane & 7) * 4);
     }
-    if (p.out.pl && p.out_planes > 0) {
-      __nv_bfloat16 hi[32], lo[32];
+  }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) split_bf16(y[j], hi[j], lo[j]);
-      uint4* dh = reinterpret_cast<uint4*>(p.out.pl + drow * p.out.ld + col0);
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&tile[i * 4 + (lane >> 3)][(lane & 7) * 4]) = a[i];
+  __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dh[j] = pack8_bf16(hi + 8 * j);
-      if (p.out_planes > 1) {
-        uint4* dl = reinterpret_cast<uint4*>(p.out.pl + (static_cast<long>(p.out.rows_alloc) + drow) * p.out.ld + col0);
+  for (int q = 0; q < 8; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(&tile[lane][4 * q]);
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+  __syncwarp();
+}
+
+// Warp-cooperative, coalesced store of 32 finished rows x 32 cols (thread <-> row) through the warp-private tile.
+// Every store instruction writes whole 128-byte lines (fp32) / whole 32-byte sectors (bf16 planes).
+__device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs& p, long row_base, int nvalid, int col0,
+                                                int lane, const float (&y)[32]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dl[j] = pack8_bf16(lo + 8 * j);
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(&tile[lane][4 * q]) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+  __syncwarp();
+  float4 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(&tile[i * 4 + (lane >> 3)][(lane & 7) * 4]);
+  const long off0 = (row_base + (lane >> 3)) * p.out.ld + col0 + (lane & 7) * 4;
+  const long step = 4L * p.out.ld;
+  if (p.out.f32) {
+    float* d = p.out.f32 + off0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i * 4 + (lane >> 3) < nvalid) *reinterpret_cast<float4*>(d + i * step) = a[i];
+  }
+  if (p.out.pl && p.out_planes > 0) {
+    __nv_bfloat16* dh = p.out.pl + off0;
+    __nv_bfloat16* dl = dh + static_cast<long>(p.out.rows_alloc) * p.out.ld;
+    const bool two = p.out_planes > 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(a[i].x, h0, l0);
+      split_bf16(a[i].y, h1, l1);
+      split_bf16(a[i].z, h2, l2);
+      split_bf16(a[i].w, h3, l3);
+      if (i * 4 + (lane >> 3) < nvalid) {
+        *reinterpret_cast<uint2*>(dh + i * step) = make_uint2(pack2_bf16(h0, h1), pack2_bf16(h2, h3));
+        if (two) *reinterpret_cast<uint2*>(dl + i * step) = make_uint2(pack2_bf16(l0, l1), pack2_bf16(l2, l3));
       }
     }
-  } else {
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < p.n_store) act_store(p.out, p.out_planes, drow, col0 + j, y[j]);
   }
+  __syncwarp();
 }
 
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, int EPI>
 __global__ void __launch_bounds__(192, 1)
 k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
   using C = TcCfg<BN, NSPLIT>;
   constexpr int STAGES = C::STAGES;
+  constexpr bool LN = (EPI == EPI_LN || EPI == EPI_LN_MOD_SILU);
   const int M = p.M_dev ? min(p.M_max, *p.M_dev) : p.M_max;
   const int tile_m = blockIdx.x;
   if (tile_m * C::BM >= M) return;  // CTA-uniform, before any barrier / allocation
@@ -214,24 +276,49 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int nkb1 = p.K1 / C::BK;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  // 1024-byte alignment for the 128B swizzle; pointer arithmetic (no integer round trip) keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* vec = reinterpret_cast<float*>(smem + C::VEC_OFF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* empty = full + STAGES;
   uint64_t* accum_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  if (threadIdx.x == 0) STAMP(0);
 
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], 1);
+  auto produce = [&](int kb) {
+    const int s = kb % STAGES;
+    tc::mbar_expect_tx(&full[s], C::STAGE_BYTES);
+    uint8_t* st = smem + s * C::STAGE_BYTES;
+    const bool first = kb < nkb1;
+    const CUtensorMap* ma = first ? &tmA : &tmA2;
+    const int kcol = (first ? kb : kb - nkb1) * C::BK;
+    const int prow = first ? p.a_plane_rows : p.a2_plane_rows;
+#pragma unroll
+    for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(st + pl * C::A_BYTES, ma, &full[s], kcol, pl * prow + tile_m * C::BM);
+#pragma unroll
+    for (int pl = 0; pl < NSPLIT; ++pl)
+      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
+  };
+
+  const int npre = nkb < STAGES ? nkb : STAGES;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        tc::mbar_init(&full[s], 1);
+        tc::mbar_init(&empty[s], 1);
+      }
+      tc::mbar_init(accum_full, 1);
+      tc::fence_barrier_init();
+      tc::fence_proxy_async();
+      // the first ring pass needs no consumer hand-shake: start the loads before the CTA-wide setup barrier
+      for (int kb = 0; kb < npre; ++kb) produce(kb);
+      STAMP(2);
     }
-    tc::mbar_init(accum_full, 1);
-    tc::fence_barrier_init();
-    tc::fence_proxy_async();
-    tc::tma_prefetch_desc(&tmA);
-    tc::tma_prefetch_desc(&tmW);
+    __syncwarp();
   }
   if (warp == 1) {
     tc::tmem_alloc(tmem_slot, BN);
@@ -241,31 +328,18 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::mbar_expect_tx(&full[s], C::STAGE_BYTES);
-        uint8_t* st = smem + s * C::STAGE_BYTES;
-        const bool first = kb < nkb1;
-        const CUtensorMap* ma = first ? &tmA : &tmA2;
-        const int kcol = (first ? kb : kb - nkb1) * C::BK;
-        const int prow = first ? p.a_plane_rows : p.a2_plane_rows;
-#pragma unroll
-        for (int pl = 0; pl < NSPLIT; ++pl)
-          tc::tma_load_2d(st + pl * C::A_BYTES, ma, &full[s], kcol, pl * prow + tile_m * C::BM);
-#pragma unroll
-        for (int pl = 0; pl < NSPLIT; ++pl)
-#pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES + c * 8192, &tmW, &full[s], kb * C::BK,
-                            pl * p.w_plane_rows + n0 + c * 64);
+      // ===== TMA producer (remaining k-blocks) =====
+      for (int kb = npre; kb < nkb; ++kb) {
+        tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
+        produce(kb);
       }
+      STAMP(3);
     }
+    __syncwarp();  // reconverge before the CTA barrier (bar.sync counts per warp)
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer (single thread) =====
@@ -275,6 +349,8 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t ph = (kb / STAGES) & 1;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
+        if (kb == 0) STAMP(4);
+        if (kb == nkb - 1) STAMP(5);
         const uint32_t sa = tc::smem_u32(smem + s * C::STAGE_BYTES);
         const uint32_t sw = sa + NSPLIT * C::A_BYTES;
 #pragma unroll
@@ -296,73 +372,360 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc::mma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
       }
       tc::mma_commit(accum_full);
+      STAMP(6);
     }
+    __syncwarp();
   } else {
     // ===== epilogue: 4 warps, thread <-> accumulator row =====
-    tc::mbar_wait(accum_full, 0);
-    tc::tc_fence_after();
+    // (1) while the mainloop runs: per-column vectors -> shared memory (read back as broadcast float4)
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < BN; i += 128) vec[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+    if (LN) {
+      for (int i = et; i < 256; i += 128) {
+        vec[256 + i] = __ldg(p.ln_g + i);
+        vec[512 + i] = __ldg(p.ln_b + i);
+        if (EPI == EPI_LN_MOD_SILU) {
+          vec[768 + i] = 1.f + __ldg(p.mod + i);
+          vec[1024 + i] = __ldg(p.mod + 256 + i);
+        }
+      }
+    }
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     const int r = wq * 32 + lane;
     const long row = static_cast<long>(tile_m) * C::BM + r;
     const bool valid = row < M;
+    const long row_base = static_cast<long>(tile_m) * C::BM + wq * 32;
+    const int nvalid = static_cast<int>(min(32L, static_cast<long>(M) - row_base));  // may be <= 0
     const long drow = (valid && p.row_map) ? p.row_map[row] : row;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+    // (2) accumulator ready
+    tc::mbar_wait(accum_full, 0);
+    tc::tc_fence_after();
+    if (threadIdx.x == 64) STAMP(7);
+    float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + wq * C::TILE_BYTES);   // aliases dead stage memory
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    float v[32];
-    if (p.epi == EPI_LN || p.epi == EPI_LN_MOD_SILU) {
+    const bool fast = (p.row_map == nullptr) && ((p.out.ld & 7) == 0);
+    float v[32], t[32];
+    if (LN) {
       // BN == 256 == N: whole row in this thread.  3 passes over TMEM (exact two-pass variance).
       float s = 0.f;
+#pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        if (EPI == EPI_LN && p.res) warp_load_rows(tile, p.res, p.ldres, nullptr, row_base, nvalid, c * 32, lane, t);
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = c * 32 + j;
-          float x = v[j] + (p.bias ? __ldg(p.bias + col) : 0.f);
-          if (p.epi == EPI_LN && p.res && valid) x += p.res[row * p.ldres + col];
-          v[j] = x;
-          s += x;
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(vec + c * 32 + 4 * q);
+          v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
         }
+        if (EPI == EPI_LN && p.res) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += t[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s += v[j];
         tc::tmem_st32(trow + c * 32, v);
       }
       const float mean = s * (1.f / 256.f);
-      float q = 0.f;
+      if (threadIdx.x == 64) STAMP(10);
+      float q2 = 0.f;
+#pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float d = v[j] - mean;
-          q += d * d;
+          q2 += d * d;
         }
       }
-      const float rstd = 1.0f / sqrtf(q * (1.f / 256.f) + LD_EPS);
-      const float* addrow = (p.epi == EPI_LN && p.addv && valid) ? p.addv + static_cast<long>(p.add_idx[row]) * p.ld_add : nullptr;
+      const float rstd = 1.0f / sqrtf(q2 * (1.f / 256.f) + LD_EPS);
+      if (threadIdx.x == 64) STAMP(11);
+#pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        if (EPI == EPI_LN && p.addv) warp_load_rows(tile, p.addv, p.ld_add, p.add_idx, row_base, nvalid, c * 32, lane, t);
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = c * 32 + j;
-          float y = (v[j] - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col);
-          if (p.epi == EPI_LN_MOD_SILU) y = silu(y * (1.f + __ldg(p.mod + col)) + __ldg(p.mod + 256 + col));
-          else if (addrow) y += addrow[col];
-          v[j] = y;
+        for (int q = 0; q < 8; ++q) {
+          const float4 g4 = *reinterpret_cast<const float4*>(vec + 256 + c * 32 + 4 * q);
+          const float4 b4 = *reinterpret_cast<const float4*>(vec + 512 + c * 32 + 4 * q);
+          v[4 * q] = (v[4 * q] - mean) * rstd * g4.x + b4.x;
+          v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * g4.y + b4.y;
+          v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * g4.z + b4.z;
+          v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * g4.w + b4.w;
         }
-        if (valid) tc_store32(p, drow, c * 32, v);
+        if (EPI == EPI_LN_MOD_SILU) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s4 = *reinterpret_cast<const float4*>(vec + 768 + c * 32 + 4 * q);
+            const float4 h4 = *reinterpret_cast<const float4*>(vec + 1024 + c * 32 + 4 * q);
+            v[4 * q] = silu(v[4 * q] * s4.x + h4.x);
+            v[4 * q + 1] = silu(v[4 * q + 1] * s4.y + h4.y);
+            v[4 * q + 2] = silu(v[4 * q + 2] * s4.z + h4.z);
+            v[4 * q + 3] = silu(v[4 * q + 3] * s4.w + h4.w);
+          }
+        } else if (p.addv) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += t[j];
+        }
+        if (fast) warp_store_rows(tile, p, row_base, nvalid, c * 32, lane, v);
+        else if (valid) tc_store32_slow(p, drow, c * 32, v);
       }
     } else {
+#pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        tc::tmem_ld32(trow + c * 32, v);
         const int col0 = n0 + c * 32;
-        if (valid && col0 < p.n_store) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            v[j] = (col < p.N) ? epi_pointwise(p, v[j], row, col) : 0.f;
+        if (col0 >= p.n_store) break;  // warp-uniform
+        const bool full_chunk = fast && (col0 + 32 <= p.n_store);
+        if (EPI == EPI_RES) {
+          if (full_chunk) {
+            warp_load_rows(tile, p.res, p.ldres, nullptr, row_base, nvalid, col0, lane, t);
+          } else {
+            for (int j = 0; j < 32; ++j) t[j] = (valid && col0 + j < p.N) ? p.res[row * p.ldres + col0 + j] : 0.f;
           }
-          tc_store32(p, drow, col0, v);
         }
+        if (threadIdx.x == 64 && c == 0) STAMP(10);
+        tc::tmem_ld32(trow + c * 32, v);
+        if (threadIdx.x == 64 && c == 0) STAMP(11);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(vec + c * 32 + 4 * q);
+          v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (EPI == EPI_RELU) v[j] = fmaxf(v[j], 0.f);
+          else if (EPI == EPI_GELU) v[j] = gelu_erf(v[j]);
+          else if (EPI == EPI_SILU) v[j] = silu(v[j]);
+          else if (EPI == EPI_RES) v[j] += t[j];
+        }
+        if (threadIdx.x == 64 && c == 0) STAMP(12);
+        if (full_chunk) warp_store_rows(tile, p, row_base, nvalid, col0, lane, v);
+        else if (valid) tc_store32_slow(p, drow, col0, v);
+        if (threadIdx.x == 64 && c == 0) STAMP(13);
       }
+    }
+    if (threadIdx.x == 64) STAMP(8);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
+#undef STAMP
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm-epilogue linears (N == 256) split over a cluster of CL CTAs along N: CTA `rank` owns 256/CL output columns
+// (its own W slice, TMEM slice and epilogue columns) and the per-row LayerNorm statistics are exchanged through
+// distributed shared memory (two exact passes: sum -> mean, centred sum of squares -> rstd).  CL x more SMs work on
+// every 128-row tile than with a whole-row CTA, which is what the latency-bound denoiser loop (10 row tiles) needs.
+template <int CL, int NSPLIT, int EPI>
+__global__ void __cluster_dims__(1, CL, 1) __launch_bounds__(192, 1)
+k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
+  constexpr int BN = 256 / CL;
+  static_assert(BN == 64 || BN == 128, "cluster split supports 2 or 4 CTAs");
+  using C = TcCfg<BN, NSPLIT>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int NCH = BN / 32;
+  const int M = p.M_dev ? min(p.M_max, *p.M_dev) : p.M_max;
+  const int tile_m = blockIdx.x;
+  if (tile_m * C::BM >= M) return;  // cluster-uniform
+  const uint32_t rank = tc::cluster_ctarank();
+  const int n0 = static_cast<int>(rank) * BN;
+  const int nkb = p.K / C::BK;
+  const int nkb1 = p.K1 / C::BK;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* vec = reinterpret_cast<float*>(smem + C::VEC_OFF);   // [0,BN) bias | [256,..) g | [512,..) b | [768,..) 1+scale | [1024,..) shift
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  // row statistics exchanged across the cluster: [2 passes][CL ranks][128 rows]; lives after the epilogue tiles in the
+  // (by then dead) stage memory is NOT possible -- peers write it while our mainloop may still run -> own region
+  float* stat = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // 2 * CL * 128 floats (<= 4 KB)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  auto produce = [&](int kb) {
+    const int s = kb % STAGES;
+    tc::mbar_expect_tx(&full[s], C::STAGE_BYTES);
+    uint8_t* st = smem + s * C::STAGE_BYTES;
+    const bool first = kb < nkb1;
+    const CUtensorMap* ma = first ? &tmA : &tmA2;
+    const int kcol = (first ? kb : kb - nkb1) * C::BK;
+    const int prow = first ? p.a_plane_rows : p.a2_plane_rows;
+#pragma unroll
+    for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(st + pl * C::A_BYTES, ma, &full[s], kcol, pl * prow + tile_m * C::BM);
+#pragma unroll
+    for (int pl = 0; pl < NSPLIT; ++pl)
+      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
+  };
+
+  const int npre = nkb < STAGES ? nkb : STAGES;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        tc::mbar_init(&full[s], 1);
+        tc::mbar_init(&empty[s], 1);
+      }
+      tc::mbar_init(accum_full, 1);
+      tc::fence_barrier_init();
+      tc::fence_proxy_async();
+      for (int kb = 0; kb < npre; ++kb) produce(kb);
+    }
+    __syncwarp();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, BN);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = npre; kb < nkb; ++kb) {
+        tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
+        produce(kb);
+      }
+    }
+    __syncwarp();
+    tc::cluster_sync();
+    tc::cluster_sync();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(C::BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        tc::mbar_wait(&full[s], (kb / STAGES) & 1);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t sw = sa + NSPLIT * C::A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < C::BK / C::UMMA_K; ++kk) {
+          const uint32_t koff = kk * C::UMMA_K * 2;
+          const uint64_t a_hi = tc::smem_desc_sw128(sa + koff);
+          const uint64_t w_hi = tc::smem_desc_sw128(sw + koff);
+          const uint32_t acc0 = (kb | kk) != 0;
+          if (NSPLIT == 1) {
+            tc::mma_bf16_ss(tmem_base, a_hi, w_hi, idesc, acc0);
+          } else {
+            const uint64_t a_lo = tc::smem_desc_sw128(sa + C::A_BYTES + koff);
+            const uint64_t w_lo = tc::smem_desc_sw128(sw + C::W_BYTES + koff);
+            tc::mma_bf16_ss(tmem_base, a_lo, w_hi, idesc, acc0);
+            tc::mma_bf16_ss(tmem_base, a_hi, w_lo, idesc, 1u);
+            tc::mma_bf16_ss(tmem_base, a_hi, w_hi, idesc, 1u);
+          }
+        }
+        tc::mma_commit(&empty[s]);
+      }
+      tc::mma_commit(accum_full);
+    }
+    __syncwarp();
+    tc::cluster_sync();
+    tc::cluster_sync();
+  } else {
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < BN; i += 128) {
+      vec[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      vec[256 + i] = __ldg(p.ln_g + n0 + i);
+      vec[512 + i] = __ldg(p.ln_b + n0 + i);
+      if (EPI == EPI_LN_MOD_SILU) {
+        vec[768 + i] = 1.f + __ldg(p.mod + n0 + i);
+        vec[1024 + i] = __ldg(p.mod + 256 + n0 + i);
+      }
+    }
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const long row_base = static_cast<long>(tile_m) * C::BM + wq * 32;
+    const int nvalid = static_cast<int>(min(32L, static_cast<long>(M) - row_base));
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    tc::mbar_wait(accum_full, 0);
+    tc::tc_fence_after();
+    float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + wq * C::TILE_BYTES);
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    float v[NCH][32], t[32];
+    // pass A: v = acc + bias (+ residual); partial row sum over this CTA's columns
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (EPI == EPI_LN && p.res) warp_load_rows(tile, p.res, p.ldres, nullptr, row_base, nvalid, n0 + c * 32, lane, t);
+      tc::tmem_ld32(trow + c * 32, v[c]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(vec + c * 32 + 4 * q);
+        v[c][4 * q] += b4.x; v[c][4 * q + 1] += b4.y; v[c][4 * q + 2] += b4.z; v[c][4 * q + 3] += b4.w;
+      }
+      if (EPI == EPI_LN && p.res) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c][j] += t[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s += v[c][j];
+    }
+    const uint32_t stat_addr = tc::smem_u32(stat);
+#pragma unroll
+    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((0 * CL + rank) * 128 + r) * 4, k), s);
+    tc::cluster_sync();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < CL; ++k) tot += stat[(0 * CL + k) * 128 + r];
+    const float mean = tot * (1.f / 256.f);
+    float q2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = v[c][j] - mean;
+        q2 += d * d;
+      }
+#pragma unroll
+    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((1 * CL + rank) * 128 + r) * 4, k), q2);
+    tc::cluster_sync();
+    float qt = 0.f;
+#pragma unroll
+    for (int k = 0; k < CL; ++k) qt += stat[(1 * CL + k) * 128 + r];
+    const float rstd = 1.0f / sqrtf(qt * (1.f / 256.f) + LD_EPS);
+    // pass C: normalise this CTA's columns and store
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (EPI == EPI_LN && p.addv) warp_load_rows(tile, p.addv, p.ld_add, p.add_idx, row_base, nvalid, n0 + c * 32, lane, t);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 g4 = *reinterpret_cast<const float4*>(vec + 256 + c * 32 + 4 * q);
+        const float4 b4 = *reinterpret_cast<const float4*>(vec + 512 + c * 32 + 4 * q);
+        v[c][4 * q] = (v[c][4 * q] - mean) * rstd * g4.x + b4.x;
+        v[c][4 * q + 1] = (v[c][4 * q + 1] - mean) * rstd * g4.y + b4.y;
+        v[c][4 * q + 2] = (v[c][4 * q + 2] - mean) * rstd * g4.z + b4.z;
+        v[c][4 * q + 3] = (v[c][4 * q + 3] - mean) * rstd * g4.w + b4.w;
+      }
+      if (EPI == EPI_LN_MOD_SILU) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(vec + 768 + c * 32 + 4 * q);
+          const float4 h4 = *reinterpret_cast<const float4*>(vec + 1024 + c * 32 + 4 * q);
+          v[c][4 * q] = silu(v[c][4 * q] * s4.x + h4.x);
+          v[c][4 * q + 1] = silu(v[c][4 * q + 1] * s4.y + h4.y);
+          v[c][4 * q + 2] = silu(v[c][4 * q + 2] * s4.z + h4.z);
+          v[c][4 * q + 3] = silu(v[c][4 * q + 3] * s4.w + h4.w);
+        }
+      } else if (p.addv) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c][j] += t[j];
+      }
+      warp_store_rows(tile, p, row_base, nvalid, n0 + c * 32, lane, v[c]);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
 }
