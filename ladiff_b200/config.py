@@ -70,10 +70,9 @@ class Cfg(dict):
         return self[k] if k in self else default
 
     def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError as e:
-            raise AttributeError(k) from e
+        if k not in self:
+            raise AttributeError(k)
+        return self[k]          # a missing ${...} target surfaces as KeyError, like OmegaConf's interpolation error
 
     def __setattr__(self, k, v):
         self[k] = v

@@ -28,6 +28,13 @@ enum Epi : int {
   EPI_SILU = 6
 };
 
+// Programmatic dependent launch: every kernel of the sampling plans starts with pdl_prologue() -- signal that the next
+// grid may begin its own prologue, then wait until the previous grid's results are visible.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 

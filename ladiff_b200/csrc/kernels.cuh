@@ -50,6 +50,7 @@ __global__ void k_fill_rows(const int* __restrict__ off, int S, int* __restrict_
 enum Unary : int { U_COPY = 0, U_RELU = 1, U_SILU = 2 };
 
 __global__ void k_unary(const float* __restrict__ in, int ld_in, int rows, int cols, int op, Act out, int planes) {
+  pdl_prologue();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long>(rows) * cols) return;
   const int r = i / cols, c = i % cols;
@@ -62,6 +63,7 @@ __global__ void k_unary(const float* __restrict__ in, int ld_in, int rows, int c
 // LayerNorm over 256 columns, one warp per row.  rows = min(rows_max, *rows_dev).
 __global__ void k_layernorm256(const float* __restrict__ in, int ld_in, int rows_max, const int* __restrict__ rows_dev,
                                const float* __restrict__ g, const float* __restrict__ b, Act out, int planes) {
+  pdl_prologue();
   const int rows = rows_dev ? min(rows_max, *rows_dev) : rows_max;
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,6 +93,7 @@ __global__ void k_layernorm256(const float* __restrict__ in, int ld_in, int rows
 // (architectures/tools/embeddings.py:245-285).  Frequencies are formed in double and rounded to fp32 so the
 // fp32 product t*f matches torch's to the last bit in almost every entry.
 __global__ void k_sinus_embed(const int* __restrict__ timesteps, int n, Act out, int planes) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 768) return;
   const int r = i / 768, c = i % 768;
@@ -109,6 +112,7 @@ __global__ void k_sinus_embed(const int* __restrict__ timesteps, int n, Act out,
 // (architectures/mdiff_transformer.py:158-162 with h = LN(y) hoisted out of the step loop).
 __global__ void k_ca_prologue(const float* __restrict__ lny, int ld_lny, const float* __restrict__ mod, int ld_mod,
                               int n_steps, int S, Act out, int planes) {
+  pdl_prologue();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long>(n_steps) * S * 256) return;
   const int c = i & 255;
@@ -123,6 +127,7 @@ __global__ void k_ca_prologue(const float* __restrict__ lny, int ld_lny, const f
 __global__ void k_pack_x(const float* __restrict__ src, int src_mod, int T, const float* __restrict__ pe,
                          const int* __restrict__ row_seq, const int* __restrict__ row_t, const int* __restrict__ R_dev,
                          Act x, int planes) {
+  pdl_prologue();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long row = i >> 8;
   const int c = i & 255;
@@ -139,6 +144,7 @@ template <int MAXT>
 __global__ void k_attn_small(const float* __restrict__ qkv, const int* __restrict__ off, int S,
                              const float* __restrict__ textkv, int ld_textkv, const float* __restrict__ timekv,
                              Act out, int planes) {
+  pdl_prologue();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int s = gw >> 2, h = gw & 3;
   if (s >= S) return;
@@ -190,6 +196,7 @@ __global__ void k_attn_small(const float* __restrict__ qkv, const int* __restric
 __global__ void k_cfg_ddim(const float* __restrict__ tok, const int* __restrict__ off, int B, int T,
                            const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ coef,
                            float guidance, float* __restrict__ lat, const float* __restrict__ pe, Act x, int planes) {
+  pdl_prologue();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int bi = gw / T, t = gw % T;
   if (bi >= B) return;
@@ -292,6 +299,7 @@ __global__ void k_z_out(const float* __restrict__ lat, const int* __restrict__ o
 // queries = 0 + pe[:L]  (architectures/ladiff_vae.py:299,334)
 __global__ void k_dec_init(const float* __restrict__ pe, const int* __restrict__ row_t, const int* __restrict__ R_dev,
                            Act x, int planes) {
+  pdl_prologue();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long row = i >> 8;
   const int c = i & 255;
@@ -301,6 +309,7 @@ __global__ void k_dec_init(const float* __restrict__ pe, const int* __restrict__
 
 // zrows[moff[b] + t, :] = z[t, b, :] for t < m[b]  (valid memory rows only)
 __global__ void k_gather_z(const float* __restrict__ z, const int* __restrict__ moff, int B, int T, Act out, int planes) {
+  pdl_prologue();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long>(B) * T * 256) return;
   const int c = i & 255;
@@ -316,6 +325,7 @@ template <int MAXT>
 __global__ void k_attn_cross(const float* __restrict__ q, const float* __restrict__ memkv, int ld_memkv, int kv_off,
                              const int* __restrict__ row_seq, const int* __restrict__ moff,
                              const int* __restrict__ R_dev, Act out, int planes) {
+  pdl_prologue();
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= *R_dev) return;
@@ -377,6 +387,7 @@ struct SelfAttnSmem {
 
 __global__ void __launch_bounds__(256) k_attn_self(const float* __restrict__ qkv, const int* __restrict__ foff, Act out,
                                                    int planes) {
+  pdl_prologue();
   extern __shared__ uint8_t sa_raw[];
   SelfAttnSmem& sm = *reinterpret_cast<SelfAttnSmem*>(sa_raw);
   const int b = blockIdx.z, h = blockIdx.y, qb = blockIdx.x;

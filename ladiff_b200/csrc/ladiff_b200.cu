@@ -35,6 +35,7 @@ struct Err {
   }
 };
 thread_local std::string g_create_error;
+bool g_use_pdl = true;
 
 #define CK(expr)                                                                                      \
   do {                                                                                                \
@@ -173,6 +174,23 @@ int alloc_act(H* h, Arena& ar, ActBuf* b, int rows, int ld, bool f32, bool plane
   return LADIFF_OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor drains and
+// synchronises itself with griddepcontrol.wait (every plan kernel begins with pdl_prologue / pdl_wait).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // launching the fused linear
 struct LinCall {
@@ -198,9 +216,8 @@ template <int BN, int NS, int EPI>
 int launch_tc_e(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int tiles_m) {
   using Cfg = TcCfg<BN, NS>;
   dim3 grid(tiles_m, (c.W->N + BN - 1) / BN);
-  k_linear_tc<BN, NS, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(c.A->map, c.A2 ? c.A2->map : c.A->map,
-                                                                         BN == 64 ? c.W->map64 : (BN == 128 ? c.W->map128 : c.W->map256), a);
-  CK(cudaGetLastError());
+  CK(launch_pdl(k_linear_tc<BN, NS, EPI>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, c.A->map, c.A2 ? c.A2->map : c.A->map,
+                BN == 64 ? c.W->map64 : (BN == 128 ? c.W->map128 : c.W->map256), a));
   h->launches++;
   return LADIFF_OK;
 }
@@ -211,9 +228,8 @@ template <int NS, int EPI>
 int launch_tc_ln(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int tiles_m) {
   using Cfg = TcCfg<256 / LN_CL, NS>;
   dim3 grid(tiles_m, LN_CL);
-  k_linear_tc_ln<LN_CL, NS, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(c.A->map, c.A2 ? c.A2->map : c.A->map,
-                                                                              LN_CL == 4 ? c.W->map64 : c.W->map128, a);
-  CK(cudaGetLastError());
+  CK(launch_pdl(k_linear_tc_ln<LN_CL, NS, EPI>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, c.A->map, c.A2 ? c.A2->map : c.A->map,
+                LN_CL == 4 ? c.W->map64 : c.W->map128, a));
   h->launches++;
   return LADIFF_OK;
 }
@@ -281,12 +297,11 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
     if (!a.A || (c.A2 && !a.A2)) return h->err.set(LADIFF_ERR_STATE, "fp32 linear: missing fp32 operand");
     if (c.M_max >= 4096) {
       dim3 grid((c.M_max + 31) / 32, (W.N + 255) / 256);
-      k_linear_simt<4><<<grid, 256, 0, st>>>(a);
+      CK(launch_pdl(k_linear_simt<4>, grid, dim3(256), 0, st, a));
     } else {
       dim3 grid((c.M_max + 15) / 16, (W.N + 255) / 256);
-      k_linear_simt<2><<<grid, 256, 0, st>>>(a);
+      CK(launch_pdl(k_linear_simt<2>, grid, dim3(256), 0, st, a));
     }
-    CK(cudaGetLastError());
     h->launches++;
     return LADIFF_OK;
   }
@@ -313,6 +328,12 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
     kernel<<<grid, block, smem, st>>>(__VA_ARGS__); \
     CK(cudaGetLastError());                         \
     h->launches++;                                  \
+  } while (0)
+
+#define LAUNCHP(kernel, grid, block, smem, st, ...)                          \
+  do {                                                                       \
+    CK(launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__));  \
+    h->launches++;                                                           \
   } while (0)
 
 inline unsigned cdiv(long a, long b) { return static_cast<unsigned>((a + b - 1) / b); }
@@ -574,13 +595,13 @@ int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg) {
 // time tables: depend on (timesteps, weights) only -> cached across calls (SURVEY.md 8a hoist table)
 int enqueue_time_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   const int n = p->n, mode = p->mode, pl = p->planes;
-  LAUNCH(k_sinus_embed, cdiv(n * 768, 256), 256, 0, st, p->ts, n, p->sin.act, pl);
+  LAUNCHP(k_sinus_embed, cdiv(n * 768, 256), 256, 0, st, p->ts, n, p->sin.act, pl);
   LinCall c;
   c.A = &p->sin; c.W = &h->time1; c.M_max = n; c.epi = EPI_SILU; c.out = p->t1.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->t1; c.W = &h->time2; c.M_max = n; c.out = p->temb.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
-  LAUNCH(k_unary, cdiv(n * 256, 256), 256, 0, st, p->temb.act.f32, 256, n, 256, (int)U_SILU, p->st.act, pl);
+  LAUNCHP(k_unary, cdiv(n * 256, 256), 256, 0, st, p->temb.act.f32, 256, n, 256, (int)U_SILU, p->st.act, pl);
   c = LinCall(); c.A = &p->temb; c.W = &h->timekv_all; c.M_max = n; c.out = f32_only(p->timekv, NL * 512);
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->st; c.W = &h->mod_all; c.M_max = n; c.out = f32_only(p->mod, NL * 1024);
@@ -591,7 +612,7 @@ int enqueue_time_tables(H* h, DenoisePlan* p, cudaStream_t st) {
 // text tables + the hoisted ca_block contribution for every (step, layer, sequence)
 int enqueue_text_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   const int S = p->S, n = p->n, mode = p->mode, pl = p->planes;
-  LAUNCH(k_unary, cdiv(static_cast<long>(S) * 768, 256), 256, 0, st, p->text768, 768, S, 768, (int)U_RELU, p->trelu.act, pl);
+  LAUNCHP(k_unary, cdiv(static_cast<long>(S) * 768, 256), 256, 0, st, p->text768, 768, S, 768, (int)U_RELU, p->trelu.act, pl);
   LinCall c;
   c.A = &p->trelu; c.W = &h->embproj; c.M_max = S; c.out = p->textp.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
@@ -599,13 +620,13 @@ int enqueue_text_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   CKS(launch_linear(h, st, mode, c));
   for (int l = 0; l < NL; ++l) {
     const DenLayerW& w = h->den[l];
-    LAUNCH(k_layernorm256, cdiv(static_cast<long>(S) * 32, 256), 256, 0, st, p->textp.act.f32, 256, S, (const int*)nullptr,
+    LAUNCHP(k_layernorm256, cdiv(static_cast<long>(S) * 32, 256), 256, 0, st, p->textp.act.f32, 256, S, (const int*)nullptr,
            w.ca_tn_g, w.ca_tn_b, p->tn.act, pl);
     float* lny = p->lny + static_cast<size_t>(l) * S * 256;
     c = LinCall(); c.A = &p->tn; c.W = &w.ca_value; c.M_max = S; c.epi = EPI_LN; c.ln_g = w.ca_sn_g; c.ln_b = w.ca_sn_b;
     c.out = f32_only(lny, 256);
     CKS(launch_linear(h, st, mode, c));
-    LAUNCH(k_ca_prologue, cdiv(static_cast<long>(n) * S * 256, 256), 256, 0, st, lny, 256, p->mod + l * 1024, NL * 1024, n, S,
+    LAUNCHP(k_ca_prologue, cdiv(static_cast<long>(n) * S * 256, 256), 256, 0, st, lny, 256, p->mod + l * 1024, NL * 1024, n, S,
            p->ca_a.act, pl);
     c = LinCall(); c.A = &p->ca_a; c.W = &w.ca_out; c.M_max = n * S;
     c.out = f32_only(p->delta + static_cast<size_t>(l) * n * S * 256, 256);
@@ -620,7 +641,7 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   LinCall c;
   c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
   CKS(launch_linear(h, st, mode, c));
-  LAUNCH(k_attn_small<8>, cdiv(static_cast<long>(S) * 4 * 32, 256), 256, 0, st, p->qkv, p->off, S, p->textkv + l * 512, NL * 512,
+  LAUNCHP(k_attn_small<8>, cdiv(static_cast<long>(S) * 4 * 32, 256), 256, 0, st, p->qkv, p->off, S, p->textkv + l * 512, NL * 512,
          p->timekv + static_cast<size_t>(step) * NL * 512 + l * 512, p->a.act, pl);
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
@@ -672,11 +693,11 @@ int enqueue_meta(H* h, cudaStream_t st, const int* cnt_host, int S, int* cnt, in
 
 int enqueue_reverse_body(H* h, DenoisePlan* p, cudaStream_t st, float guidance) {
   CKS(enqueue_text_tables(h, p, st));
-  LAUNCH(k_pack_x, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, p->lat, p->B, p->T, h->den_pe, p->row_seq, p->row_t, p->R,
+  LAUNCHP(k_pack_x, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, p->lat, p->B, p->T, h->den_pe, p->row_seq, p->row_t, p->R,
          p->xin.act, p->planes);
   for (int step = 0; step < p->n; ++step) {
     CKS(enqueue_den_tokens(h, p, st, step));
-    LAUNCH(k_cfg_ddim, cdiv(static_cast<long>(p->B) * p->T * 32, 256), 256, 0, st, p->xa.act.f32, p->off, p->B, p->T, h->den_fg, h->den_fb,
+    LAUNCHP(k_cfg_ddim, cdiv(static_cast<long>(p->B) * p->T * 32, 256), 256, 0, st, p->xa.act.f32, p->off, p->B, p->T, h->den_fg, h->den_fb,
            p->coef + 2 * step, guidance, p->lat, h->den_pe, p->xin.act, p->planes);
   }
   return LADIFF_OK;
@@ -746,14 +767,14 @@ int enqueue_dec_layer(H* h, DecodePlan* p, cudaStream_t st, int l, const ActBuf&
   CKS(launch_linear(h, st, mode, c));
   {
     dim3 grid((p->Lmax + SA_QB - 1) / SA_QB, 4, p->B);
-    LAUNCH(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, p->qkv, p->foff, p->a.act, pl);
+    LAUNCHP(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, p->qkv, p->foff, p->a.act, pl);
   }
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->x1; c.W = &w.q2; c.M_max = R; c.M_dev = p->Rf; c.out = f32_only(p->q2, 256);
   CKS(launch_linear(h, st, mode, c));
-  LAUNCH(k_attn_cross<8>, cdiv(static_cast<long>(R) * 32, 256), 256, 0, st, p->q2, p->memkv, NL * 512, l * 512, p->frow_seq, p->moff, p->Rf,
+  LAUNCHP(k_attn_cross<8>, cdiv(static_cast<long>(R) * 32, 256), 256, 0, st, p->q2, p->memkv, NL * 512, l * 512, p->frow_seq, p->moff, p->Rf,
          p->a.act, pl);
   c = LinCall(); c.A = &p->a; c.W = &w.out2; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = p->x1.act.f32;
   c.ln_g = w.n2g; c.ln_b = w.n2b; c.out = p->x2.act; c.out_planes = pl;
@@ -769,11 +790,11 @@ int enqueue_dec_layer(H* h, DecodePlan* p, cudaStream_t st, int l, const ActBuf&
 // everything of vae.decode between the staged latent z and the final LayerNorm'd tokens (p->xn)
 int enqueue_decode_body(H* h, DecodePlan* p, cudaStream_t st) {
   const int pl = p->planes, mode = p->mode;
-  LAUNCH(k_gather_z, cdiv(static_cast<long>(p->Mmax) * 256, 256), 256, 0, st, p->z, p->moff, p->B, p->T, p->zrows.act, pl);
+  LAUNCHP(k_gather_z, cdiv(static_cast<long>(p->Mmax) * 256, 256), 256, 0, st, p->z, p->moff, p->B, p->T, p->zrows.act, pl);
   LinCall c;
   c.A = &p->zrows; c.W = &h->memkv_all; c.M_max = p->Mmax; c.M_dev = p->Rm; c.out = f32_only(p->memkv, NL * 512);
   CKS(launch_linear(h, st, mode, c));
-  LAUNCH(k_dec_init, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, h->dec_pe, p->frow_t, p->Rf, p->x0.act, pl);
+  LAUNCHP(k_dec_init, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, h->dec_pe, p->frow_t, p->Rf, p->x0.act, pl);
   const ActBuf* x = &p->x0;
   for (int i = 0; i < 4; ++i) {
     CKS(enqueue_dec_layer(h, p, st, i, *x, p->skip[i]));
@@ -787,7 +808,7 @@ int enqueue_decode_body(H* h, DecodePlan* p, cudaStream_t st) {
     CKS(launch_linear(h, st, mode, c));
     CKS(enqueue_dec_layer(h, p, st, 5 + i, p->xb, p->xa));
   }
-  LAUNCH(k_layernorm256, cdiv(static_cast<long>(p->Rmax) * 32, 256), 256, 0, st, p->xa.act.f32, 256, p->Rmax, p->Rf, h->dec_fg, h->dec_fb,
+  LAUNCHP(k_layernorm256, cdiv(static_cast<long>(p->Rmax) * 32, 256), 256, 0, st, p->xa.act.f32, 256, p->Rmax, p->Rf, h->dec_fg, h->dec_fb,
          p->xn.act, pl);
   return LADIFF_OK;
 }
@@ -879,6 +900,7 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   }
   std::unique_ptr<ladiff_handle> h(new ladiff_handle());
   h->cfg = *cfg;
+  g_use_pdl = getenv("LADIFF_NO_PDL") == nullptr;
   cudaGetDevice(&h->device);
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, h->device);
@@ -1042,7 +1064,7 @@ int ladiff_denoiser_forward(ladiff_handle* h, const float* sample_dev, int32_t t
   CK(cudaMemcpyAsync(p->ts, &timestep, sizeof(int), cudaMemcpyHostToDevice, st));
   CKS(enqueue_time_tables(h, p, st));
   CKS(enqueue_text_tables(h, p, st));
-  LAUNCH(k_pack_x, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, sample_dev, S, T, h->den_pe, p->row_seq, p->row_t, p->R,
+  LAUNCHP(k_pack_x, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, sample_dev, S, T, h->den_pe, p->row_seq, p->row_t, p->R,
          p->xin.act, p->planes);
   CKS(enqueue_den_tokens(h, p, st, 0));
   LAUNCH(k_final_ln_out, cdiv(static_cast<long>(S) * T * 32, 256), 256, 0, st, p->xa.act.f32, p->off, S, T, h->den_fg, h->den_fb, out_dev);
@@ -1129,7 +1151,7 @@ int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const float* W_dev,
   const int planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
   ActBuf a;
   CKS(alloc_act(h, ar, &a, M, K, true, planes > 0));
-  LAUNCH(k_unary, cdiv(static_cast<long>(M) * K, 256), 256, 0, st, A_dev, K, M, K, (int)U_COPY, a.act, planes);
+  LAUNCHP(k_unary, cdiv(static_cast<long>(M) * K, 256), 256, 0, st, A_dev, K, M, K, (int)U_COPY, a.act, planes);
   LinCall c;
   c.A = &a; c.W = &w; c.M_max = M; c.epi = epilogue; c.res = res_dev; c.ldres = N; c.ln_g = ln_g_dev; c.ln_b = ln_b_dev; c.mod = mod_dev;
   c.out = f32_only(out_dev, N);
@@ -1162,7 +1184,7 @@ int ladiff_linear_bench(ladiff_handle* h, int32_t M, int32_t N, int32_t K, int32
   ActBuf a, o;
   CKS(alloc_act(h, ar, &a, M, K, true, planes > 0));
   CKS(alloc_act(h, ar, &o, M, N, true, planes > 0));
-  LAUNCH(k_unary, cdiv(static_cast<long>(M) * K, 256), 256, 0, st, Asrc, K, M, K, (int)U_COPY, a.act, planes);
+  LAUNCHP(k_unary, cdiv(static_cast<long>(M) * K, 256), 256, 0, st, Asrc, K, M, K, (int)U_COPY, a.act, planes);
   LinCall c;
   c.A = &a; c.W = &w; c.M_max = M; c.epi = epilogue; c.res = res; c.ldres = N; c.ln_g = vec; c.ln_b = vec + 256; c.mod = vec + 512;
   c.out = o.act; c.out_planes = planes;

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) k_linear_simt(const LinArgs p) {
   constexpr int BM = 8 * RPW, BK = 32;
   __shared__ float As[BM][BK + 1];
   __shared__ float Ws[BK][256];
+  pdl_prologue();
   const int M = p.M_dev ? min(p.M_max, *p.M_dev) : p.M_max;
   const int row0 = blockIdx.x * BM;
   if (row0 >= M) return;
@@ -270,7 +271,8 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr bool LN = (EPI == EPI_LN || EPI == EPI_LN_MOD_SILU);
   const int M = p.M_dev ? min(p.M_max, *p.M_dev) : p.M_max;
   const int tile_m = blockIdx.x;
-  if (tile_m * C::BM >= M) return;  // CTA-uniform, before any barrier / allocation
+  tc::pdl_launch_dependents();
+  if (tile_m * C::BM >= M || (p.dbg_flags & 2)) return;  // CTA-uniform, before any barrier / allocation
   const int n0 = blockIdx.y * BN;
   const int nkb = p.K / C::BK;
   const int nkb1 = p.K1 / C::BK;
@@ -289,9 +291,17 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 0) STAMP(0);
 
-  auto produce = [&](int kb) {
+  // weights never depend on the previous grid, activations do: the W half of a stage may be requested before pdl_wait
+  auto produce_w = [&](int kb) {
     const int s = kb % STAGES;
     tc::mbar_expect_tx(&full[s], C::STAGE_BYTES);
+    uint8_t* st = smem + s * C::STAGE_BYTES;
+#pragma unroll
+    for (int pl = 0; pl < NSPLIT; ++pl)
+      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
+  };
+  auto produce_a = [&](int kb) {
+    const int s = kb % STAGES;
     uint8_t* st = smem + s * C::STAGE_BYTES;
     const bool first = kb < nkb1;
     const CUtensorMap* ma = first ? &tmA : &tmA2;
@@ -299,9 +309,6 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int prow = first ? p.a_plane_rows : p.a2_plane_rows;
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(st + pl * C::A_BYTES, ma, &full[s], kcol, pl * prow + tile_m * C::BM);
-#pragma unroll
-    for (int pl = 0; pl < NSPLIT; ++pl)
-      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
   };
 
   const int npre = nkb < STAGES ? nkb : STAGES;
@@ -315,7 +322,9 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc::fence_barrier_init();
       tc::fence_proxy_async();
       // the first ring pass needs no consumer hand-shake: start the loads before the CTA-wide setup barrier
-      for (int kb = 0; kb < npre; ++kb) produce(kb);
+      for (int kb = 0; kb < npre; ++kb) produce_w(kb);
+      tc::pdl_wait();
+      for (int kb = 0; kb < npre; ++kb) produce_a(kb);
       STAMP(2);
     }
     __syncwarp();
@@ -335,7 +344,8 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // ===== TMA producer (remaining k-blocks) =====
       for (int kb = npre; kb < nkb; ++kb) {
         tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
-        produce(kb);
+        produce_w(kb);
+        produce_a(kb);
       }
       STAMP(3);
     }
@@ -384,10 +394,13 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int i = et; i < 256; i += 128) {
         vec[256 + i] = __ldg(p.ln_g + i);
         vec[512 + i] = __ldg(p.ln_b + i);
-        if (EPI == EPI_LN_MOD_SILU) {
-          vec[768 + i] = 1.f + __ldg(p.mod + i);
-          vec[1024 + i] = __ldg(p.mod + 256 + i);
-        }
+      }
+    }
+    tc::pdl_wait();  // everything below may belong to earlier grids (modulation table, residuals, outputs)
+    if (EPI == EPI_LN_MOD_SILU) {
+      for (int i = et; i < 256; i += 128) {
+        vec[768 + i] = 1.f + p.mod[i];
+        vec[1024 + i] = p.mod[256 + i];
       }
     }
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
@@ -531,7 +544,8 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int NCH = BN / 32;
   const int M = p.M_dev ? min(p.M_max, *p.M_dev) : p.M_max;
   const int tile_m = blockIdx.x;
-  if (tile_m * C::BM >= M) return;  // cluster-uniform
+  tc::pdl_launch_dependents();
+  if (tile_m * C::BM >= M || (p.dbg_flags & 2)) return;  // cluster-uniform
   const uint32_t rank = tc::cluster_ctarank();
   const int n0 = static_cast<int>(rank) * BN;
   const int nkb = p.K / C::BK;
@@ -550,9 +564,17 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  auto produce = [&](int kb) {
+  // weights never depend on the previous grid, activations do: the W half of a stage may be requested before pdl_wait
+  auto produce_w = [&](int kb) {
     const int s = kb % STAGES;
     tc::mbar_expect_tx(&full[s], C::STAGE_BYTES);
+    uint8_t* st = smem + s * C::STAGE_BYTES;
+#pragma unroll
+    for (int pl = 0; pl < NSPLIT; ++pl)
+      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
+  };
+  auto produce_a = [&](int kb) {
+    const int s = kb % STAGES;
     uint8_t* st = smem + s * C::STAGE_BYTES;
     const bool first = kb < nkb1;
     const CUtensorMap* ma = first ? &tmA : &tmA2;
@@ -560,9 +582,6 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int prow = first ? p.a_plane_rows : p.a2_plane_rows;
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(st + pl * C::A_BYTES, ma, &full[s], kcol, pl * prow + tile_m * C::BM);
-#pragma unroll
-    for (int pl = 0; pl < NSPLIT; ++pl)
-      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
   };
 
   const int npre = nkb < STAGES ? nkb : STAGES;
@@ -575,7 +594,9 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::mbar_init(accum_full, 1);
       tc::fence_barrier_init();
       tc::fence_proxy_async();
-      for (int kb = 0; kb < npre; ++kb) produce(kb);
+      for (int kb = 0; kb < npre; ++kb) produce_w(kb);
+      tc::pdl_wait();
+      for (int kb = 0; kb < npre; ++kb) produce_a(kb);
     }
     __syncwarp();
   }
@@ -592,7 +613,8 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       for (int kb = npre; kb < nkb; ++kb) {
         tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
-        produce(kb);
+        produce_w(kb);
+        produce_a(kb);
       }
     }
     __syncwarp();
@@ -636,9 +658,12 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       vec[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
       vec[256 + i] = __ldg(p.ln_g + n0 + i);
       vec[512 + i] = __ldg(p.ln_b + n0 + i);
-      if (EPI == EPI_LN_MOD_SILU) {
-        vec[768 + i] = 1.f + __ldg(p.mod + n0 + i);
-        vec[1024 + i] = __ldg(p.mod + 256 + n0 + i);
+    }
+    tc::pdl_wait();
+    if (EPI == EPI_LN_MOD_SILU) {
+      for (int i = et; i < BN; i += 128) {
+        vec[768 + i] = 1.f + p.mod[n0 + i];
+        vec[1024 + i] = p.mod[256 + n0 + i];
       }
     }
     const int wq = warp & 3;

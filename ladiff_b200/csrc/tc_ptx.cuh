@@ -145,6 +145,12 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// wait(): blocks until the grids this launch depends on have completed and their memory is visible (no-op without a
+// programmatic dependency).  launch_dependents(): lets the next grid in the stream / graph start its prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- thread-block clusters / distributed shared memory -------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
