@@ -4,14 +4,15 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// row bookkeeping: cnt[S] (rows per sequence) -> off[S+1] (exclusive prefix), total, row -> (seq, t) maps
-__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ cnt, int S, int* __restrict__ off,
+// row bookkeeping: cnt[S] (rows per sequence) -> off[S+1] (exclusive prefix), total, row -> (seq, t) maps.
+// Sequence i takes cnt[i % mod] rows (mod = S: plain; mod = B: the CFG-doubled batch shares one m[B] vector).
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ cnt, int S, int mod, int* __restrict__ off,
                                                       int* __restrict__ total) {
   __shared__ int part[1024];
   const int chunk = (S + 1023) / 1024;
   const int b = threadIdx.x * chunk, e = min(S, b + chunk);
   int s = 0;
-  for (int i = b; i < e; ++i) s += cnt[i];
+  for (int i = b; i < e; ++i) s += cnt[i % mod];
   part[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ cn
   int run = part[threadIdx.x];
   for (int i = b; i < e; ++i) {
     off[i] = run;
-    run += cnt[i];
+    run += cnt[i % mod];
   }
 }
 
@@ -58,6 +59,17 @@ __global__ void k_unary(const float* __restrict__ in, int ld_in, int rows, int c
   if (op == U_RELU) v = fmaxf(v, 0.f);
   else if (op == U_SILU) v = silu(v);
   act_store(out, planes, r, c, v);
+}
+
+// emb_proj's ReLU (architectures/ladiff_denoiser.py:72-73) on the text rows of one chain of prompts [b0, b0+Bc):
+// chain row r < Bc is the uncond row b0+r of src [2*Btot,768], row Bc+r the cond row Btot+b0+r (ladiff.py:258-264).
+__global__ void k_text_relu(const float* __restrict__ src, int Btot, int b0, int Bc, Act out, int planes) {
+  pdl_prologue();
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= 2L * Bc * 768) return;
+  const int r = i / 768, c = i % 768;
+  const long sr = r < Bc ? b0 + r : static_cast<long>(Btot) + b0 + (r - Bc);
+  act_store(out, planes, r, c, fmaxf(src[sr * 768 + c], 0.f));
 }
 
 // LayerNorm over 256 columns, one warp per row.  rows = min(rows_max, *rows_dev).
@@ -284,13 +296,13 @@ __global__ void k_final_ln_out(const float* __restrict__ tok, const int* __restr
 }
 
 // z[t, b, :] = t < m[b] ? lat[b, t, :] : 0      (ladiff.py:500 permute + :562-566 re-zeroing)
-__global__ void k_z_out(const float* __restrict__ lat, const int* __restrict__ off, int B, int T, float* __restrict__ z) {
+__global__ void k_z_out(const float* __restrict__ lat, const int* __restrict__ cnt, int B, int T, float* __restrict__ z) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long>(B) * T * 256) return;
   const int c = i & 255;
   const long bt = i >> 8;
   const int t = bt % T, b = bt / T;
-  const int m = off[b + 1] - off[b];
+  const int m = cnt[b];
   z[(static_cast<long>(t) * B + b) * 256 + c] = (t < m) ? lat[i] : 0.f;
 }
 

@@ -102,7 +102,9 @@ struct DecLayerW {
 };
 
 struct DenoisePlan;
+struct ReversePlan;
 struct DecodePlan;
+constexpr int MAX_CHAINS = 8;
 
 }  // namespace
 
@@ -125,8 +127,11 @@ struct ladiff_handle {
   Weight dec_skip[4], dec_final, memkv_all;
   float *dec_fg = nullptr, *dec_fb = nullptr, *dec_pe = nullptr;
   std::map<std::string, std::unique_ptr<DenoisePlan>> den_plans;
+  std::map<std::string, std::unique_ptr<ReversePlan>> rev_plans;
   std::map<std::string, std::unique_ptr<DecodePlan>> dec_plans;
   cudaStream_t cap_stream = nullptr;
+  cudaStream_t side[MAX_CHAINS] = {};       // forked streams of the chained reverse loop
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
 };
 
 namespace {
@@ -536,6 +541,10 @@ struct DenoisePlan {
   // activations
   ActBuf xin, xa, xb, x1, x3, skip[4], a, hbuf, sbuf;
   float* qkv = nullptr;
+  // chained use (ReversePlan): inputs live in the parent's staging buffers, time tables are shared with chain 0
+  const float* text_src = nullptr;  // parent text [2*Btot,768]; this chain covers prompts [b0, b0+B)
+  int text_Btot = 0, b0 = 0;
+  const int* cnt_src = nullptr;     // parent m[Btot] + b0
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
   ~DenoisePlan() {
@@ -543,9 +552,29 @@ struct DenoisePlan {
   }
 };
 
+// LADIFF._diffusion_reverse for one (B, steps, mode, guidance): the batch is cut into independent chains of prompts
+// (sequences never interact), each with its own workspace, enqueued on forked streams inside ONE captured graph so that
+// the latency-bound per-chain kernel sequences overlap on the 148 SMs.
+struct ReversePlan {
+  Arena ar;
+  int B = 0, n = 0, mode = 0;
+  int* cnt = nullptr;        // m[B]
+  float* text768 = nullptr;  // [2B,768]
+  float* lat = nullptr;      // [B,T,256]
+  std::vector<std::unique_ptr<DenoisePlan>> chains;
+  std::vector<int> cached_ts;
+  std::vector<float> cached_coef;
+  cudaGraphExec_t exec = nullptr;
+  int64_t graph_launches = 0;
+  ~ReversePlan() {
+    if (exec) cudaGraphExecDestroy(exec);
+  }
+};
+
 Act f32_only(float* p, int ld) { return Act{p, nullptr, ld, 0}; }
 
-int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg) {
+int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg, float* ext_lat = nullptr,
+                       const DenoisePlan* tables = nullptr) {
   p->S = S;
   p->B = cfg ? S / 2 : 0;
   p->n = n;
@@ -562,16 +591,27 @@ int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg) {
   CK(ar.alloc((void**)&p->R, sizeof(int)));
   CK(ar.alloc((void**)&p->row_seq, R * sizeof(int)));
   CK(ar.alloc((void**)&p->row_t, R * sizeof(int)));
-  CK(ar.alloc((void**)&p->ts, n * sizeof(int)));
-  CK(ar.alloc((void**)&p->coef, 2 * n * sizeof(float)));
-  CK(ar.alloc((void**)&p->text768, static_cast<size_t>(S) * 768 * sizeof(float)));
-  if (cfg) CK(ar.alloc((void**)&p->lat, static_cast<size_t>(p->B) * p->T * 256 * sizeof(float)));
-  CKS(alloc_act(h, ar, &p->sin, n, 768, f, tcm));
-  CKS(alloc_act(h, ar, &p->t1, n, 256, f, tcm));
-  CKS(alloc_act(h, ar, &p->temb, n, 256, true, tcm));
-  CKS(alloc_act(h, ar, &p->st, n, 256, f, tcm));
-  CK(ar.alloc((void**)&p->timekv, static_cast<size_t>(n) * NL * 512 * sizeof(float)));
-  CK(ar.alloc((void**)&p->mod, static_cast<size_t>(n) * NL * 1024 * sizeof(float)));
+  if (tables) {  // step-only tables are identical for every chain of a ReversePlan
+    p->ts = tables->ts;
+    p->coef = tables->coef;
+    p->timekv = tables->timekv;
+    p->mod = tables->mod;
+  } else {
+    CK(ar.alloc((void**)&p->ts, n * sizeof(int)));
+    CK(ar.alloc((void**)&p->coef, 2 * n * sizeof(float)));
+    CKS(alloc_act(h, ar, &p->sin, n, 768, f, tcm));
+    CKS(alloc_act(h, ar, &p->t1, n, 256, f, tcm));
+    CKS(alloc_act(h, ar, &p->temb, n, 256, true, tcm));
+    CKS(alloc_act(h, ar, &p->st, n, 256, f, tcm));
+    CK(ar.alloc((void**)&p->timekv, static_cast<size_t>(n) * NL * 512 * sizeof(float)));
+    CK(ar.alloc((void**)&p->mod, static_cast<size_t>(n) * NL * 1024 * sizeof(float)));
+  }
+  if (ext_lat) {
+    p->lat = ext_lat;
+  } else {
+    CK(ar.alloc((void**)&p->text768, static_cast<size_t>(S) * 768 * sizeof(float)));
+    if (cfg) CK(ar.alloc((void**)&p->lat, static_cast<size_t>(p->B) * p->T * 256 * sizeof(float)));
+  }
   CKS(alloc_act(h, ar, &p->trelu, S, 768, f, tcm));
   CKS(alloc_act(h, ar, &p->textp, S, 256, true, tcm));
   CKS(alloc_act(h, ar, &p->tn, S, 256, f, tcm));
@@ -612,7 +652,10 @@ int enqueue_time_tables(H* h, DenoisePlan* p, cudaStream_t st) {
 // text tables + the hoisted ca_block contribution for every (step, layer, sequence)
 int enqueue_text_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   const int S = p->S, n = p->n, mode = p->mode, pl = p->planes;
-  LAUNCHP(k_unary, cdiv(static_cast<long>(S) * 768, 256), 256, 0, st, p->text768, 768, S, 768, (int)U_RELU, p->trelu.act, pl);
+  if (p->text_src)
+    LAUNCHP(k_text_relu, cdiv(static_cast<long>(S) * 768, 256), 256, 0, st, p->text_src, p->text_Btot, p->b0, p->B, p->trelu.act, pl);
+  else
+    LAUNCHP(k_unary, cdiv(static_cast<long>(S) * 768, 256), 256, 0, st, p->text768, 768, S, 768, (int)U_RELU, p->trelu.act, pl);
   LinCall c;
   c.A = &p->trelu; c.W = &h->embproj; c.M_max = S; c.out = p->textp.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
@@ -686,7 +729,7 @@ int enqueue_den_tokens(H* h, DenoisePlan* p, cudaStream_t st, int step) {
 int enqueue_meta(H* h, cudaStream_t st, const int* cnt_host, int S, int* cnt, int* off, int* R, int* row_seq, int* row_t,
                  int* row_dst, int dst_stride) {
   CK(cudaMemcpyAsync(cnt, cnt_host, S * sizeof(int), cudaMemcpyHostToDevice, st));
-  LAUNCH(k_scan_counts, 1, 1024, 0, st, cnt, S, off, R);
+  LAUNCH(k_scan_counts, 1, 1024, 0, st, cnt, S, S, off, R);
   LAUNCH(k_fill_rows, cdiv(static_cast<long>(S) * 32, 256), 256, 0, st, off, S, row_seq, row_t, row_dst, dst_stride);
   return LADIFF_OK;
 }
@@ -699,6 +742,66 @@ int enqueue_reverse_body(H* h, DenoisePlan* p, cudaStream_t st, float guidance) 
     CKS(enqueue_den_tokens(h, p, st, step));
     LAUNCHP(k_cfg_ddim, cdiv(static_cast<long>(p->B) * p->T * 32, 256), 256, 0, st, p->xa.act.f32, p->off, p->B, p->T, h->den_fg, h->den_fb,
            p->coef + 2 * step, guidance, p->lat, h->den_pe, p->xin.act, p->planes);
+  }
+  return LADIFF_OK;
+}
+
+// all chains of a ReversePlan: chain 0 on `st`, the others on forked side streams joined back into `st`
+int enqueue_reverse_chains(H* h, ReversePlan* rp, cudaStream_t st, float guidance) {
+  const int nch = static_cast<int>(rp->chains.size());
+  if (nch > 1) {
+    if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->ev_fork, st));
+  }
+  for (int c = 0; c < nch; ++c) {
+    DenoisePlan* p = rp->chains[c].get();
+    cudaStream_t sc = st;
+    if (c > 0) {
+      if (!h->side[c]) CK(cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking));
+      if (!h->ev_join[c]) CK(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
+      sc = h->side[c];
+      CK(cudaStreamWaitEvent(sc, h->ev_fork, 0));
+    }
+    LAUNCH(k_scan_counts, 1, 1024, 0, sc, p->cnt_src, p->S, p->B, p->off, p->R);
+    LAUNCH(k_fill_rows, cdiv(static_cast<long>(p->S) * 32, 256), 256, 0, sc, p->off, p->S, p->row_seq, p->row_t, (int*)nullptr, 0);
+    CKS(enqueue_reverse_body(h, p, sc, guidance));
+    if (c > 0) {
+      CK(cudaEventRecord(h->ev_join[c], sc));
+      CK(cudaStreamWaitEvent(st, h->ev_join[c], 0));
+    }
+  }
+  return LADIFF_OK;
+}
+
+int pick_chains(int B) {
+  if (const char* e = getenv("LADIFF_CHAINS")) {
+    int v = atoi(e);
+    if (v >= 1) return v > MAX_CHAINS ? MAX_CHAINS : (v > B ? B : v);
+  }
+  // one chain should keep >= 2 row tiles of 128 (CFG-doubled, <= 5 rows per sequence): 32 prompts -> 320 rows
+  int n = B / 32;
+  return n < 1 ? 1 : (n > 4 ? 4 : n);
+}
+
+int build_reverse_plan(H* h, ReversePlan* rp, int B, int n, int mode) {
+  rp->B = B;
+  rp->n = n;
+  rp->mode = mode;
+  const int T = h->cfg.max_it;
+  CK(rp->ar.alloc((void**)&rp->cnt, B * sizeof(int)));
+  CK(rp->ar.alloc((void**)&rp->text768, static_cast<size_t>(2 * B) * 768 * sizeof(float)));
+  CK(rp->ar.alloc((void**)&rp->lat, static_cast<size_t>(B) * T * 256 * sizeof(float)));
+  const int nch = pick_chains(B);
+  for (int c = 0; c < nch; ++c) {
+    const int b0 = static_cast<int>(static_cast<long>(B) * c / nch), b1 = static_cast<int>(static_cast<long>(B) * (c + 1) / nch);
+    std::unique_ptr<DenoisePlan> p(new DenoisePlan());
+    CKS(build_denoise_plan(h, p.get(), 2 * (b1 - b0), n, mode, true, rp->lat + static_cast<size_t>(b0) * T * 256,
+                           c ? rp->chains[0].get() : nullptr));
+    p->text_src = rp->text768;
+    p->text_Btot = B;
+    p->b0 = b0;
+    p->cnt_src = rp->cnt + b0;
+    rp->chains.push_back(std::move(p));
   }
   return LADIFF_OK;
 }
@@ -935,9 +1038,15 @@ void ladiff_destroy(ladiff_handle* h) {
   if (!h) return;
   cudaDeviceSynchronize();
   h->den_plans.clear();
+  h->rev_plans.clear();
   h->dec_plans.clear();
   for (auto& kv : h->raw) cudaFree(kv.second.dev);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  for (int c = 0; c < MAX_CHAINS; ++c) {
+    if (h->side[c]) cudaStreamDestroy(h->side[c]);
+    if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 
@@ -966,6 +1075,7 @@ int ladiff_finalize_weights(ladiff_handle* h, int32_t which, void* stream) {
   CK(cudaDeviceSynchronize());  // plans may still be in flight
   if (which & 1) {
     h->den_plans.clear();
+    h->rev_plans.clear();
     CKS(finalize_denoiser(h, st));
   }
   if (which & 2) {
@@ -986,49 +1096,51 @@ int ladiff_diffusion_reverse(ladiff_handle* h, const float* text_emb_dev, const 
   if (!text_emb_dev || !lengths_host || !noise_dev || !timesteps_host || !c1_host || !c2_host || !z_out_dev || B < 1 || n_steps < 1)
     return h->err.set(LADIFF_ERR_INVALID, "ladiff_diffusion_reverse: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int T = h->cfg.max_it, S = 2 * B;
+  const int T = h->cfg.max_it;
   uint32_t gbits;
   memcpy(&gbits, &guidance_scale, 4);
   char key[96];
   snprintf(key, sizeof(key), "cfg:%d:%d:%d:%08x", B, n_steps, mode, gbits);
-  auto& slot = h->den_plans[key];
+  auto& slot = h->rev_plans[key];
   if (!slot) {
-    slot.reset(new DenoisePlan());
-    int s = build_denoise_plan(h, slot.get(), S, n_steps, mode, true);
+    slot.reset(new ReversePlan());
+    int s = build_reverse_plan(h, slot.get(), B, n_steps, mode);
     if (s != LADIFF_OK) {
-      h->den_plans.erase(key);
+      h->rev_plans.erase(key);
       return s;
     }
   }
-  DenoisePlan* p = slot.get();
-  // ---- per-call meta (ragged row layout lives on the device)
-  std::vector<int> cnt(S);
+  ReversePlan* rp = slot.get();
+  // ---- per-call inputs staged at fixed addresses (the captured graph reads them); the ragged row layout is derived on
+  // the device inside the graph
+  std::vector<int> cnt(B);
   for (int b = 0; b < B; ++b) {
     if (lengths_host[b] < 1) return h->err.set(LADIFF_ERR_INVALID, "lengths[%d] = %d", b, lengths_host[b]);
     int m = (lengths_host[b] + h->cfg.frame_per_latent - 1) / h->cfg.frame_per_latent;
-    cnt[b] = cnt[b + B] = m < T ? m : T;
+    cnt[b] = m < T ? m : T;
   }
-  CKS(enqueue_meta(h, st, cnt.data(), S, p->cnt, p->off, p->R, p->row_seq, p->row_t, nullptr, 0));
-  CK(cudaMemcpyAsync(p->text768, text_emb_dev, static_cast<size_t>(S) * 768 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(p->lat, noise_dev, static_cast<size_t>(B) * T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  // ---- schedule-dependent tables (cached)
+  CK(cudaMemcpyAsync(rp->cnt, cnt.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(rp->text768, text_emb_dev, static_cast<size_t>(2 * B) * 768 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(rp->lat, noise_dev, static_cast<size_t>(B) * T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // ---- schedule-dependent tables (cached; shared by all chains)
   std::vector<int> ts(timesteps_host, timesteps_host + n_steps);
   std::vector<float> coef(2 * n_steps);
   for (int i = 0; i < n_steps; ++i) {
     coef[2 * i] = c1_host[i];
     coef[2 * i + 1] = c2_host[i];
   }
-  if (ts != p->cached_ts || coef != p->cached_coef) {
-    CK(cudaStreamSynchronize(st));  // previous users of the tables
-    CK(cudaMemcpyAsync(p->ts, ts.data(), n_steps * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(p->coef, coef.data(), 2 * n_steps * sizeof(float), cudaMemcpyHostToDevice, st));
-    CKS(enqueue_time_tables(h, p, st));
+  if (ts != rp->cached_ts || coef != rp->cached_coef) {
+    DenoisePlan* p0 = rp->chains[0].get();
+    CK(cudaDeviceSynchronize());  // previous users of the tables (any stream)
+    CK(cudaMemcpyAsync(p0->ts, ts.data(), n_steps * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p0->coef, coef.data(), 2 * n_steps * sizeof(float), cudaMemcpyHostToDevice, st));
+    CKS(enqueue_time_tables(h, p0, st));
     CK(cudaStreamSynchronize(st));
-    p->cached_ts = ts;
-    p->cached_coef = coef;
+    rp->cached_ts = ts;
+    rp->cached_coef = coef;
   }
-  CKS(run_graphed(h, st, &p->exec, &p->graph_launches, [&](cudaStream_t s) { return enqueue_reverse_body(h, p, s, guidance_scale); }));
-  LAUNCH(k_z_out, cdiv(static_cast<long>(B) * T * 256, 256), 256, 0, st, p->lat, p->off, B, T, z_out_dev);
+  CKS(run_graphed(h, st, &rp->exec, &rp->graph_launches, [&](cudaStream_t s) { return enqueue_reverse_chains(h, rp, s, guidance_scale); }));
+  LAUNCH(k_z_out, cdiv(static_cast<long>(B) * T * 256, 256), 256, 0, st, rp->lat, rp->cnt, B, T, z_out_dev);
   return LADIFF_OK;
 }
 
