@@ -37,6 +37,19 @@ __device__ __forceinline__ void pdl_prologue() {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// Branch-free erf-GELU for the tensor-core epilogues (erff's range split serialises the 32 independent elements a thread
+// owns).  erf by Abramowitz & Stegun 7.1.26: |erf error| <= 1.5e-7, far below the bf16x3 product error (~1e-5 relative).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;  // 1 / (1 + p z): MUFU.RCP (<= 1 ulp here; __frcp_rn would add a branchy IEEE fix-up path)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -53,6 +66,16 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// Packed variant for two neighbouring columns (x in the low half): F2FP.BF16.F32.PACK_AB runs on the full-rate pipes,
+// the scalar F2F.BF16.F32 conversion does not.  Same round-to-nearest-even results as split_bf16.
+__device__ __forceinline__ void split2_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float xf = __uint_as_float(hi << 16), yf = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - xf, y - yf);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // nplanes: 0 none, 1 hi only, 2 hi + lo

@@ -486,6 +486,183 @@ __global__ void __launch_bounds__(256) k_attn_self(const float* __restrict__ qkv
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ragged decoder self-attention on the tensor pipe (tensor-core modes).  CTA = (head, sequence), 8 warps; K and V^T of the
+// (sequence, head) are staged ONCE in shared memory as bf16 hi/lo planes, each warp owns 16-query tiles and keeps the whole
+// score row block S[16, L<=NT*8] in registers (no online softmax needed at L <= 256): S = Q K^T by mma.sync.m16n8k16
+// (bf16 x bf16 -> fp32), fp32 softmax in registers, P re-used directly as the A fragments of P V.  NSPLIT = 2 forms every
+// product from hi/lo split operands (lo*hi + hi*lo + hi*hi, fp32 accumulate) like the bf16x3 GEMMs, so the attention keeps
+// fp32-grade accuracy; NSPLIT = 1 is the plain bf16 mode.  Nothing is computed or stored for padded frames.
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) { split2_bf16(x, y, hi, lo); }
+
+#define SAT_KLD 72  // bf16 per K row (64 + 8 pad): B-fragment reads are bank-conflict free
+
+template <int NT>
+constexpr int sat_smem_bytes(int nsplit) { return nsplit * (NT * 8 * SAT_KLD + 64 * (NT * 8 + 8)) * 2; }
+
+template <int NT, int NSPLIT>
+__global__ void __launch_bounds__(256, 1) k_attn_self_tc(const float* __restrict__ qkv, const int* __restrict__ foff,
+                                                         Act out, int planes) {
+  constexpr int KP = NT * 8;        // padded key capacity
+  constexpr int VLD = KP + 8;       // bf16 per V^T row
+  pdl_prologue();
+  extern __shared__ uint8_t sat_raw[];
+  uint32_t* Kh = reinterpret_cast<uint32_t*>(sat_raw);            // [KP][SAT_KLD/2] words
+  uint32_t* Vh = Kh + KP * SAT_KLD / 2;                           // [64][VLD/2] words
+  uint32_t* Kl = Vh + 64 * VLD / 2;
+  uint32_t* Vl = Kl + KP * SAT_KLD / 2;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int r0 = foff[b], L = min(foff[b + 1] - r0, KP);
+  if (L <= 0) return;
+  const int Lp = (L + 15) & ~15;    // keys processed (multiple of 16); keys in [L, Lp) are zero-filled and masked
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- stage K (row-major, d contiguous) and V^T (key contiguous) as bf16 hi/lo
+  for (int i = threadIdx.x; i < Lp * 32; i += 256) {
+    const int key = i >> 5, dp = i & 31;
+    float2 k = make_float2(0.f, 0.f);
+    if (key < L) k = *reinterpret_cast<const float2*>(qkv + static_cast<long>(r0 + key) * 768 + 256 + h * 64 + 2 * dp);
+    uint32_t hi, lo;
+    split_pack2(k.x, k.y, hi, lo);
+    Kh[key * (SAT_KLD / 2) + dp] = hi;
+    if (NSPLIT > 1) Kl[key * (SAT_KLD / 2) + dp] = lo;
+  }
+  for (int i = threadIdx.x; i < (Lp / 2) * 64; i += 256) {
+    const int d = i & 63, jp = i >> 6;
+    const float* vp = qkv + static_cast<long>(r0 + 2 * jp) * 768 + 512 + h * 64 + d;
+    const float v0 = (2 * jp < L) ? vp[0] : 0.f;
+    const float v1 = (2 * jp + 1 < L) ? vp[768] : 0.f;
+    uint32_t hi, lo;
+    split_pack2(v0, v1, hi, lo);
+    Vh[d * (VLD / 2) + jp] = hi;
+    if (NSPLIT > 1) Vl[d * (VLD / 2) + jp] = lo;
+  }
+  __syncthreads();
+
+  for (int qt = warp; qt * 16 < L; qt += 8) {
+    const int q0 = qt * 16;
+    // ---- Q fragments (scaled by 1/sqrt(64) = 2^-3: exact, commutes with the split)
+    uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {      // rows g / g+8
+        const int qr = q0 + g + 8 * half;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {          // k = 2t / 2t+8
+          float2 q = make_float2(0.f, 0.f);
+          if (qr < L) q = *reinterpret_cast<const float2*>(qkv + static_cast<long>(r0 + qr) * 768 + h * 64 + kk * 16 + kh * 8 + 2 * t);
+          split_pack2(q.x * 0.125f, q.y * 0.125f, qh[kk][half + 2 * kh], ql[kk][half + 2 * kh]);
+        }
+      }
+    }
+    // ---- S = Q K^T
+    float s[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (nt * 8 < Lp) {
+        const uint32_t* kh_ = Kh + (nt * 8 + g) * (SAT_KLD / 2) + t;
+        const uint32_t* kl_ = Kl + (nt * 8 + g) * (SAT_KLD / 2) + t;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t bh0 = kh_[kk * 8], bh1 = kh_[kk * 8 + 4];
+          if (NSPLIT > 1) {
+            const uint32_t bl0 = kl_[kk * 8], bl1 = kl_[kk * 8 + 4];
+            mma16816(s[nt], ql[kk], bh0, bh1);
+            mma16816(s[nt], qh[kk], bl0, bl1);
+          }
+          mma16816(s[nt], qh[kk], bh0, bh1);
+        }
+      }
+    }
+    // ---- softmax over the L valid keys (rows g and g+8 of the tile)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 < Lp) {
+        const int key = nt * 8 + 2 * t;
+        if (key >= L) s[nt][0] = s[nt][2] = -INFINITY;
+        if (key + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 < Lp) {
+        s[nt][0] = expf(s[nt][0] - mx0);
+        s[nt][1] = expf(s[nt][1] - mx0);
+        s[nt][2] = expf(s[nt][2] - mx1);
+        s[nt][3] = expf(s[nt][3] - mx1);
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // ---- O = P V  (P fragments straight from the S accumulators)
+    float o[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < NT / 2; ++ks) {
+      if (ks * 16 < Lp) {
+        uint32_t ph[4], pl[4];
+        split_pack2(s[2 * ks][0], s[2 * ks][1], ph[0], pl[0]);
+        split_pack2(s[2 * ks][2], s[2 * ks][3], ph[1], pl[1]);
+        split_pack2(s[2 * ks + 1][0], s[2 * ks + 1][1], ph[2], pl[2]);
+        split_pack2(s[2 * ks + 1][2], s[2 * ks + 1][3], ph[3], pl[3]);
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+          const uint32_t* vh_ = Vh + (nd * 8 + g) * (VLD / 2) + ks * 8 + t;
+          const uint32_t bh0 = vh_[0], bh1 = vh_[4];
+          if (NSPLIT > 1) {
+            const uint32_t* vl_ = Vl + (nd * 8 + g) * (VLD / 2) + ks * 8 + t;
+            const uint32_t bl0 = vl_[0], bl1 = vl_[4];
+            mma16816(o[nd], pl, bh0, bh1);
+            mma16816(o[nd], ph, bl0, bl1);
+          }
+          mma16816(o[nd], ph, bh0, bh1);
+        }
+      }
+    }
+    // ---- normalise and store (fp32 master and/or bf16 planes)
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int qr = q0 + g + 8 * half;
+      if (qr >= L) continue;
+      const float inv = half ? inv1 : inv0;
+      const long base = static_cast<long>(r0 + qr) * out.ld + h * 64 + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        const float x = o[nd][2 * half] * inv, y = o[nd][2 * half + 1] * inv;
+        if (out.f32) *reinterpret_cast<float2*>(out.f32 + base + nd * 8) = make_float2(x, y);
+        if (out.pl && planes > 0) {
+          uint32_t hi, lo;
+          split_pack2(x, y, hi, lo);
+          *reinterpret_cast<uint32_t*>(out.pl + base + nd * 8) = hi;
+          if (planes > 1) *reinterpret_cast<uint32_t*>(out.pl + static_cast<long>(out.rows_alloc) * out.ld + base + nd * 8) = lo;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing: W [N, K] (row stride ldw) fp32 -> Wt [K][N] fp32 and bf16 planes [2][n_pad][K] (zero padded rows)
 __global__ void k_pack_weight(const float* __restrict__ W, int ldw, int N, int K, int n_pad, float* __restrict__ Wt,
                               __nv_bfloat16* __restrict__ pl) {
@@ -501,6 +678,34 @@ __global__ void k_pack_weight(const float* __restrict__ W, int ldw, int N, int K
   split_bf16(v, hi, lo);
   pl[i] = hi;
   pl[static_cast<long>(n_pad) * K + i] = lo;
+}
+
+// Weight folding at load time (finalize): C[n, k2] = sum_k1 A[n, k1] * B[k1, k2]  (fp32 in, fp64 accumulate, fp32 out).
+// Used to pre-multiply consecutive nn.Linear weights ([out, in] row-major: y = x W^T, so (W_b W_a) applies a then b).
+__global__ void k_fold_matmul(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int N, int K1,
+                              int K2, float* __restrict__ C, int ldc) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(N) * K2) return;
+  const int n = i / K2, k2 = i % K2;
+  double acc = 0.0;
+  for (int k = 0; k < K1; ++k) acc += static_cast<double>(A[static_cast<long>(n) * lda + k]) * static_cast<double>(B[static_cast<long>(k) * ldb + k2]);
+  C[static_cast<long>(n) * ldc + k2] = static_cast<float>(acc);
+}
+// out[n] = sum_k A[n, k] * v[k] + (b ? b[n] : 0)
+__global__ void k_fold_matvec(const float* __restrict__ A, int lda, const float* __restrict__ v, const float* __restrict__ b,
+                              int N, int K, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double acc = b ? static_cast<double>(b[n]) : 0.0;
+  for (int k = 0; k < K; ++k) acc += static_cast<double>(A[static_cast<long>(n) * lda + k]) * static_cast<double>(v[k]);
+  out[n] = static_cast<float>(acc);
+}
+// strided 2-D copy of fp32 blocks (assembling folded weight matrices)
+__global__ void k_copy2d(const float* __restrict__ src, int lds, int rows, int cols, float* __restrict__ dst, int ldd) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(rows) * cols) return;
+  const int r = i / cols, c = i % cols;
+  dst[static_cast<long>(r) * ldd + c] = src[static_cast<long>(r) * lds + c];
 }
 
 // deterministic pseudo-random fill in [-scale, scale] (benchmark operands)

@@ -36,6 +36,7 @@ struct Err {
 };
 thread_local std::string g_create_error;
 bool g_use_pdl = true;
+bool g_skip_pdl_once = false;  // next launch_pdl() uses a full dependency (kernel right after a cross-stream join)
 
 #define CK(expr)                                                                                      \
   do {                                                                                                \
@@ -121,6 +122,10 @@ struct ladiff_handle {
   // denoiser
   DenLayerW den[NL];
   Weight den_skip[4], time1, time2, embproj, timekv_all, textkv_all, mod_all;
+  // folded transitions: qkv of layer l+1 straight from (x3, s[, skip]) of layer l, and the skip merge
+  // straight from (x3, s, skip) -- the residual GEMM and the skip Linear leave the critical path
+  Weight den_qkv_fold[NL];   // [l] for l = 1..8: K = 512 (l <= 4) or 768 (l >= 5)
+  Weight den_xb_fold[4];     // skip merge i: [S1 | S1 P | S2], K = 768
   float *den_fg = nullptr, *den_fb = nullptr, *den_pe = nullptr;
   // decoder
   DecLayerW dec[NL];
@@ -131,6 +136,8 @@ struct ladiff_handle {
   std::map<std::string, std::unique_ptr<DecodePlan>> dec_plans;
   cudaStream_t cap_stream = nullptr;
   cudaStream_t side[MAX_CHAINS] = {};       // forked streams of the chained reverse loop
+  cudaStream_t aux[MAX_CHAINS] = {};        // per-chain side branch (off-critical-path residual / skip GEMMs)
+  cudaEvent_t ev_aux_fork[MAX_CHAINS] = {}, ev_aux_join[MAX_CHAINS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
 };
 
@@ -190,7 +197,8 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = (g_use_pdl && !g_skip_pdl_once) ? 1 : 0;
+  g_skip_pdl_once = false;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -200,7 +208,9 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 // launching the fused linear
 struct LinCall {
   const ActBuf* A = nullptr;
-  const ActBuf* A2 = nullptr;  // second K source (skip merge)
+  const ActBuf* A2 = nullptr;  // second K source (skip merge / folded branches)
+  const ActBuf* A3 = nullptr;  // third K source
+  bool no_pdl = false;         // launch with a full dependency (first kernel after a cross-stream join)
   const Weight* W = nullptr;
   int M_max = 0;
   const int* M_dev = nullptr;
@@ -222,7 +232,7 @@ int launch_tc_e(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int t
   using Cfg = TcCfg<BN, NS>;
   dim3 grid(tiles_m, (c.W->N + BN - 1) / BN);
   CK(launch_pdl(k_linear_tc<BN, NS, EPI>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, c.A->map, c.A2 ? c.A2->map : c.A->map,
-                BN == 64 ? c.W->map64 : (BN == 128 ? c.W->map128 : c.W->map256), a));
+                c.A3 ? c.A3->map : c.A->map, BN == 64 ? c.W->map64 : (BN == 128 ? c.W->map128 : c.W->map256), a));
   h->launches++;
   return LADIFF_OK;
 }
@@ -234,7 +244,7 @@ int launch_tc_ln(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int 
   using Cfg = TcCfg<256 / LN_CL, NS>;
   dim3 grid(tiles_m, LN_CL);
   CK(launch_pdl(k_linear_tc_ln<LN_CL, NS, EPI>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, c.A->map, c.A2 ? c.A2->map : c.A->map,
-                LN_CL == 4 ? c.W->map64 : c.W->map128, a));
+                c.A3 ? c.A3->map : c.A->map, LN_CL == 4 ? c.W->map64 : c.W->map128, a));
   h->launches++;
   return LADIFF_OK;
 }
@@ -263,6 +273,7 @@ int launch_tc(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int til
 }
 
 int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
+  if (c.no_pdl) g_skip_pdl_once = true;
   LinArgs a;
   memset(&a, 0, sizeof(a));
   const Weight& W = *c.W;
@@ -271,12 +282,16 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
   a.N = W.N;
   a.K = W.K;
   a.K1 = c.A2 ? c.A->act.ld : W.K;
-  if (c.A2 && (c.A->act.ld + c.A2->act.ld != W.K)) return h->err.set(LADIFF_ERR_INVALID, "two-source linear: K mismatch");
-  if (!c.A2 && c.A->act.ld != W.K) return h->err.set(LADIFF_ERR_INVALID, "linear: A width %d != K %d", c.A->act.ld, W.K);
+  a.K2 = c.A3 ? a.K1 + c.A2->act.ld : W.K;
+  if (c.A3 && !c.A2) return h->err.set(LADIFF_ERR_INVALID, "linear: third source without a second");
+  if (c.A->act.ld + (c.A2 ? c.A2->act.ld : 0) + (c.A3 ? c.A3->act.ld : 0) != W.K)
+    return h->err.set(LADIFF_ERR_INVALID, "linear: source widths do not add up to K %d", W.K);
   a.A = c.A->act.f32;
   a.lda = c.A->act.ld;
   a.A2 = c.A2 ? c.A2->act.f32 : nullptr;
   a.lda2 = c.A2 ? c.A2->act.ld : 0;
+  a.A3 = c.A3 ? c.A3->act.f32 : nullptr;
+  a.lda3 = c.A3 ? c.A3->act.ld : 0;
   a.Wt = W.Wt;
   a.ldw = W.N;
   a.bias = W.bias;
@@ -299,7 +314,7 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
   if (ln && W.N != 256) return h->err.set(LADIFF_ERR_INVALID, "LayerNorm epilogue needs N == 256");
   if (c.M_max <= 0) return LADIFF_OK;
   if (mode == LADIFF_MODE_FP32) {
-    if (!a.A || (c.A2 && !a.A2)) return h->err.set(LADIFF_ERR_STATE, "fp32 linear: missing fp32 operand");
+    if (!a.A || (c.A2 && !a.A2) || (c.A3 && !a.A3)) return h->err.set(LADIFF_ERR_STATE, "fp32 linear: missing fp32 operand");
     if (c.M_max >= 4096) {
       dim3 grid((c.M_max + 31) / 32, (W.N + 255) / 256);
       CK(launch_pdl(k_linear_simt<4>, grid, dim3(256), 0, st, a));
@@ -310,17 +325,20 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
     h->launches++;
     return LADIFF_OK;
   }
-  if (!c.A->has_map || (c.A2 && !c.A2->has_map)) return h->err.set(LADIFF_ERR_STATE, "tensor-core linear: operand has no bf16 planes");
-  if (W.K % 64 != 0 || a.K1 % 64 != 0) return h->err.set(LADIFF_ERR_INVALID, "tensor-core linear: K must be a multiple of 64");
+  if (!c.A->has_map || (c.A2 && !c.A2->has_map) || (c.A3 && !c.A3->has_map))
+    return h->err.set(LADIFF_ERR_STATE, "tensor-core linear: operand has no bf16 planes");
+  if (W.K % 64 != 0 || a.K1 % 64 != 0 || a.K2 % 64 != 0) return h->err.set(LADIFF_ERR_INVALID, "tensor-core linear: K must be a multiple of 64");
   a.a_plane_rows = c.A->act.rows_alloc;
   a.a2_plane_rows = c.A2 ? c.A2->act.rows_alloc : 0;
+  a.a3_plane_rows = c.A3 ? c.A3->act.rows_alloc : 0;
   a.w_plane_rows = W.n_pad;
   const int tiles_m = (c.M_max + 127) / 128;
+  // one CTA per SM (the stage ring takes ~190 KB): keep the grid within ONE wave of the 148 SMs, as narrow as that allows
   int bn = 256;
   if (!ln) {
-    const int sm2 = 2 * 148;
-    if (tiles_m * ((W.N + 63) / 64) <= sm2) bn = 64;
-    else if (tiles_m * ((W.N + 127) / 128) <= sm2) bn = 128;
+    const int sms = getenv("LADIFF_TILE_SMS") ? atoi(getenv("LADIFF_TILE_SMS")) : 148;
+    if (tiles_m * ((W.N + 63) / 64) <= (mode == LADIFF_MODE_BF16 ? 2 : 1) * sms) bn = 64;  // bf16: two 64-wide CTAs fit per SM
+    else if (tiles_m * ((W.N + 127) / 128) <= sms) bn = 128;
   }
   const bool split = (mode == LADIFF_MODE_BF16X3);
   if (bn == 256) return split ? launch_tc<256, 2>(h, st, c, a, tiles_m) : launch_tc<256, 1>(h, st, c, a, tiles_m);
@@ -414,6 +432,62 @@ int pack_concat(H* h, cudaStream_t st, Weight* w, const std::vector<std::pair<co
   return s;
 }
 
+// Folded layer transitions.  With Y_l = x3 + s P_l^T + p_l (StylizationBlock out-projection + residual,
+// mdiff_transformer.py:162,262) the next layer's in-projection is linear in (x3, s):
+//   l+1 <= 4:  qkv = x3 Wq^T + s (Wq P_l)^T + (Wq p_l + bq)
+//   l+1 >= 5:  X = Y_l S1^T + skip S2^T + sb  (cat + Linear(512->256), cross_attention.py:79-81), so
+//              qkv = x3 (Wq S1)^T + s (Wq S1 P_l)^T + skip (Wq S2)^T + (Wq (S1 p_l + sb) + bq)
+//              X   = x3 S1^T + s (S1 P_l)^T + skip S2^T + (S1 p_l + sb)
+// Products are formed once here (fp64 accumulate) and packed like any other weight; K sources are ordered (x3, s, skip).
+int fold_denoiser_transitions(H* h, cudaStream_t st) {
+  const int D = 256;
+  const std::string P = "denoiser.encoder.";
+  float *tmp = nullptr, *tb = nullptr, *m1 = nullptr, *v1 = nullptr;
+  CK(cudaMalloc(&tmp, 768ull * 768 * sizeof(float)));
+  CK(cudaMalloc(&tb, 768 * sizeof(float)));
+  CK(cudaMalloc(&m1, 768ull * 256 * sizeof(float)));
+  CK(cudaMalloc(&v1, 256 * sizeof(float)));
+  auto done = [&](int s) {
+    cudaStreamSynchronize(st);
+    cudaFree(tmp); cudaFree(tb); cudaFree(m1); cudaFree(v1);
+    return s;
+  };
+  for (int l = 0; l + 1 < NL; ++l) {
+    const Raw *Pw, *Pb, *Wq, *bq;
+    int s_;
+    if ((s_ = get_raw(h, P + block_name(l) + ".ffn.proj_out.out_layers.2.weight", {D, D}, &Pw)) != LADIFF_OK) return done(s_);
+    if ((s_ = get_raw(h, P + block_name(l) + ".ffn.proj_out.out_layers.2.bias", {D}, &Pb)) != LADIFF_OK) return done(s_);
+    if ((s_ = get_raw(h, P + block_name(l + 1) + ".sa_block.self_attn.in_proj_weight", {3 * D, D}, &Wq)) != LADIFF_OK) return done(s_);
+    if ((s_ = get_raw(h, P + block_name(l + 1) + ".sa_block.self_attn.in_proj_bias", {3 * D}, &bq)) != LADIFF_OK) return done(s_);
+    if (l + 1 <= 4) {
+      const int K = 2 * D;
+      LAUNCH(k_copy2d, cdiv(768L * D, 256), 256, 0, st, Wq->dev, D, 768, D, tmp, K);
+      LAUNCH(k_fold_matmul, cdiv(768L * D, 256), 256, 0, st, Wq->dev, D, Pw->dev, D, 768, D, D, tmp + D, K);
+      LAUNCH(k_fold_matvec, cdiv(768, 256), 256, 0, st, Wq->dev, D, Pb->dev, bq->dev, 768, D, tb);
+      if ((s_ = pack_weight(h, *h->warena, st, &h->den_qkv_fold[l + 1], tmp, K, 768, K, tb)) != LADIFF_OK) return done(s_);
+    } else {
+      const int i = l - 4, K = 3 * D;
+      const Raw *S, *sb;
+      if ((s_ = get_raw(h, P + "linear_blocks." + std::to_string(i) + ".weight", {D, 2 * D}, &S)) != LADIFF_OK) return done(s_);
+      if ((s_ = get_raw(h, P + "linear_blocks." + std::to_string(i) + ".bias", {D}, &sb)) != LADIFF_OK) return done(s_);
+      // skip merge: [S1 | S1 P | S2], bias S1 p + sb
+      LAUNCH(k_copy2d, cdiv(256L * D, 256), 256, 0, st, S->dev, 2 * D, D, D, tmp, K);
+      LAUNCH(k_fold_matmul, cdiv(256L * D, 256), 256, 0, st, S->dev, 2 * D, Pw->dev, D, D, D, D, tmp + D, K);
+      LAUNCH(k_copy2d, cdiv(256L * D, 256), 256, 0, st, S->dev + D, 2 * D, D, D, tmp + 2 * D, K);
+      LAUNCH(k_fold_matvec, 1, 256, 0, st, S->dev, 2 * D, Pb->dev, sb->dev, D, D, v1);
+      if ((s_ = pack_weight(h, *h->warena, st, &h->den_xb_fold[i], tmp, K, D, K, v1)) != LADIFF_OK) return done(s_);
+      CK(cudaStreamSynchronize(st));
+      // in-projection of the merged tokens: Wq [S1 | S1 P | S2], bias Wq (S1 p + sb) + bq ; m1 = [S1 | S1 P | S2] (256 x 768) is tmp
+      CK(cudaMemcpyAsync(m1, tmp, 256ull * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      LAUNCH(k_fold_matmul, cdiv(768L * K, 256), 256, 0, st, Wq->dev, D, m1, K, 768, D, K, tmp, K);
+      LAUNCH(k_fold_matvec, cdiv(768, 256), 256, 0, st, Wq->dev, D, v1, bq->dev, 768, D, tb);
+      if ((s_ = pack_weight(h, *h->warena, st, &h->den_qkv_fold[l + 1], tmp, K, 768, K, tb)) != LADIFF_OK) return done(s_);
+    }
+    CK(cudaStreamSynchronize(st));
+  }
+  return done(LADIFF_OK);
+}
+
 int finalize_denoiser(H* h, cudaStream_t st) {
   const int D = 256;
   h->den_ready = false;
@@ -469,6 +543,7 @@ int finalize_denoiser(H* h, cudaStream_t st) {
     mods.push_back({fw, fb});
   }
   for (int i = 0; i < 4; ++i) CKS(pack_linear(h, st, &h->den_skip[i], P + "encoder.linear_blocks." + std::to_string(i), D, 2 * D));
+  CKS(fold_denoiser_transitions(h, st));
   // K/V rows of every layer's in_proj: the conditioning tokens are step- or prompt-invariant
   CKS(pack_concat(h, st, &h->timekv_all, inproj, D, 2 * D, D));
   h->textkv_all = h->timekv_all;  // same matrix, applied to the text projection
@@ -543,7 +618,7 @@ struct DenoisePlan {
   float* qkv = nullptr;
   // chained use (ReversePlan): inputs live in the parent's staging buffers, time tables are shared with chain 0
   const float* text_src = nullptr;  // parent text [2*Btot,768]; this chain covers prompts [b0, b0+B)
-  int text_Btot = 0, b0 = 0;
+  int text_Btot = 0, b0 = 0, chain = 0;
   const int* cnt_src = nullptr;     // parent m[Btot] + b0
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
@@ -678,16 +753,19 @@ int enqueue_text_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   return LADIFF_OK;
 }
 
-int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, const ActBuf& in, const ActBuf& out) {
+// One denoiser layer after its in-projection (p->qkv holds q|k|v of the layer input `in`): sa_block attention -> out-proj +
+// residual + LN -> ReLU FFN (+LN, + hoisted ca_block delta) -> GELU FFN -> Stylization prologue.  Leaves x3 (p->x3) and
+// s (p->sbuf); the layer output Y = x3 + s P^T + p is formed by the caller (folded into the next layer, see
+// fold_denoiser_transitions).  `join` (optional) is an event the residual `in` depends on (side branch).
+int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, const ActBuf& in, cudaEvent_t join) {
   const DenLayerW& w = h->den[l];
   const int mode = p->mode, pl = p->planes, R = p->Rmax, S = p->S, n = p->n;
   LinCall c;
-  c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
-  CKS(launch_linear(h, st, mode, c));
   LAUNCHP(k_attn_small<8>, cdiv(static_cast<long>(S) * 4 * 32, 256), 256, 0, st, p->qkv, p->off, S, p->textkv + l * 512, NL * 512,
          p->timekv + static_cast<size_t>(step) * NL * 512 + l * 512, p->a.act, pl);
+  if (join) CK(cudaStreamWaitEvent(st, join, 0));
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = in.act.f32;
-  c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
+  c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl; c.no_pdl = join != nullptr;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
@@ -702,26 +780,55 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   c.ln_g = w.ffn_sn_g; c.ln_b = w.ffn_sn_b; c.mod = p->mod + static_cast<size_t>(step) * NL * 1024 + l * 1024 + 512;
   c.out = p->sbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
-  c = LinCall(); c.A = &p->sbuf; c.W = &w.ffn_out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RES; c.res = p->x3.act.f32;
-  c.out = out.act; c.out_planes = pl;
-  CKS(launch_linear(h, st, mode, c));
   return LADIFF_OK;
 }
 
-// SkipTransformerEncoder wiring (operator/cross_attention.py:69-85); tokens end up in p->xa
+// SkipTransformerEncoder wiring (operator/cross_attention.py:69-85); the last layer's tokens end up in p->xa.
+// Critical path per layer: qkv (folded) -> attention -> out-proj+LN -> FFN1 -> FFN2+LN -> FFN1' -> FFN2'+Stylization.
+// The layer outputs Y_l (l < 4, kept for the skip connections) and the merged tokens X_{l+1} (l >= 4) are only needed as
+// the residual of the NEXT layer's out-proj, so their GEMMs run on a side stream (graph branch) meanwhile.
 int enqueue_den_tokens(H* h, DenoisePlan* p, cudaStream_t st, int step) {
-  const ActBuf* x = &p->xin;
-  for (int i = 0; i < 4; ++i) {
-    CKS(enqueue_den_layer(h, p, st, i, step, *x, p->skip[i]));
-    x = &p->skip[i];
-  }
-  CKS(enqueue_den_layer(h, p, st, 4, step, *x, p->xa));
-  for (int i = 0; i < 4; ++i) {
-    LinCall c;
-    c.A = &p->xa; c.A2 = &p->skip[3 - i]; c.W = &h->den_skip[i]; c.M_max = p->Rmax; c.M_dev = p->R;
-    c.out = p->xb.act; c.out_planes = p->planes;
-    CKS(launch_linear(h, st, p->mode, c));
-    CKS(enqueue_den_layer(h, p, st, 5 + i, step, p->xb, p->xa));
+  const int mode = p->mode, pl = p->planes, R = p->Rmax;
+  const int ci = p->chain;
+  if (!h->aux[ci]) CK(cudaStreamCreateWithFlags(&h->aux[ci], cudaStreamNonBlocking));
+  if (!h->ev_aux_fork[ci]) CK(cudaEventCreateWithFlags(&h->ev_aux_fork[ci], cudaEventDisableTiming));
+  if (!h->ev_aux_join[ci]) CK(cudaEventCreateWithFlags(&h->ev_aux_join[ci], cudaEventDisableTiming));
+  cudaStream_t aux = h->aux[ci];
+  LinCall c;
+  c.A = &p->xin; c.W = &h->den[0].qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
+  CKS(launch_linear(h, st, mode, c));
+  const ActBuf* x = &p->xin;  // layer input (residual of the out-proj)
+  bool pending = false;       // side branch in flight
+  for (int l = 0; l < NL; ++l) {
+    CKS(enqueue_den_layer(h, p, st, l, step, *x, pending ? h->ev_aux_join[ci] : nullptr));
+    pending = false;
+    const DenLayerW& w = h->den[l];
+    if (l == NL - 1) {  // last layer: Y_8 itself (input of encoder.norm in k_cfg_ddim / k_final_ln_out)
+      c = LinCall(); c.A = &p->sbuf; c.W = &w.ffn_out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RES; c.res = p->x3.act.f32;
+      c.out = f32_only(p->xa.act.f32, 256);
+      CKS(launch_linear(h, st, mode, c));
+      break;
+    }
+    // ---- side branch: next layer's input tokens
+    CK(cudaEventRecord(h->ev_aux_fork[ci], st));
+    CK(cudaStreamWaitEvent(aux, h->ev_aux_fork[ci], 0));
+    if (l < 4) {
+      c = LinCall(); c.A = &p->sbuf; c.W = &w.ffn_out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RES; c.res = p->x3.act.f32;
+      c.out = p->skip[l].act; c.out_planes = pl; c.no_pdl = true;  // planes too: third K source of the mirrored layer's folds
+      CKS(launch_linear(h, aux, mode, c));
+      x = &p->skip[l];
+    } else {
+      c = LinCall(); c.A = &p->x3; c.A2 = &p->sbuf; c.A3 = &p->skip[7 - l]; c.W = &h->den_xb_fold[l - 4]; c.M_max = R; c.M_dev = p->R;
+      c.out = f32_only(p->xb.act.f32, 256); c.no_pdl = true;
+      CKS(launch_linear(h, aux, mode, c));
+      x = &p->xb;
+    }
+    CK(cudaEventRecord(h->ev_aux_join[ci], aux));
+    pending = true;
+    // ---- critical path: in-projection of layer l+1 straight from (x3, s[, skip])
+    c = LinCall(); c.A = &p->x3; c.A2 = &p->sbuf; if (l >= 4) c.A3 = &p->skip[7 - l];
+    c.W = &h->den_qkv_fold[l + 1]; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
+    CKS(launch_linear(h, st, mode, c));
   }
   return LADIFF_OK;
 }
@@ -778,8 +885,10 @@ int pick_chains(int B) {
     int v = atoi(e);
     if (v >= 1) return v > MAX_CHAINS ? MAX_CHAINS : (v > B ? B : v);
   }
-  // one chain should keep >= 2 row tiles of 128 (CFG-doubled, <= 5 rows per sequence): 32 prompts -> 320 rows
-  int n = B / 32;
+  // Measured on B200 (profiles/r01b_chains.txt): at B = 128 every link is latency-bound and a chain of 32 prompts takes as
+  // long as one of 128, so splitting gains nothing; at B = 1024 four chains of 256 prompts overlap one chain's epilogues /
+  // launch gaps with another's mainloops (reverse 107 -> 84 ms).
+  int n = B / 256;
   return n < 1 ? 1 : (n > 4 ? 4 : n);
 }
 
@@ -801,6 +910,7 @@ int build_reverse_plan(H* h, ReversePlan* rp, int B, int n, int mode) {
     p->text_Btot = B;
     p->b0 = b0;
     p->cnt_src = rp->cnt + b0;
+    p->chain = c;
     rp->chains.push_back(std::move(p));
   }
   return LADIFF_OK;
@@ -868,9 +978,20 @@ int enqueue_dec_layer(H* h, DecodePlan* p, cudaStream_t st, int l, const ActBuf&
   LinCall c;
   c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->Rf; c.out = f32_only(p->qkv, 768);
   CKS(launch_linear(h, st, mode, c));
-  {
+  if (mode == LADIFF_MODE_FP32 || getenv("LADIFF_ATTN_SIMT")) {
     dim3 grid((p->Lmax + SA_QB - 1) / SA_QB, 4, p->B);
     LAUNCHP(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, p->qkv, p->foff, p->a.act, pl);
+  } else {
+    // tensor-core modes: (head, sequence) CTAs, hi/lo split products in bf16x3 mode
+    dim3 grid(4, p->B);
+    const bool big = p->Lmax > 26 * 8;
+    if (mode == LADIFF_MODE_BF16X3) {
+      if (big) LAUNCHP((k_attn_self_tc<32, 2>), grid, 256, sat_smem_bytes<32>(2), st, p->qkv, p->foff, p->a.act, pl);
+      else LAUNCHP((k_attn_self_tc<26, 2>), grid, 256, sat_smem_bytes<26>(2), st, p->qkv, p->foff, p->a.act, pl);
+    } else {
+      if (big) LAUNCHP((k_attn_self_tc<32, 1>), grid, 256, sat_smem_bytes<32>(1), st, p->qkv, p->foff, p->a.act, pl);
+      else LAUNCHP((k_attn_self_tc<26, 1>), grid, 256, sat_smem_bytes<26>(1), st, p->qkv, p->foff, p->a.act, pl);
+    }
   }
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
@@ -1020,6 +1141,10 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   }
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(k_attn_self, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelfAttnSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<32>(2));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(2));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<32>(1));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(1));
   if (e == cudaSuccess) e = set_tc_attr<256, 2>();
   if (e == cudaSuccess) e = set_tc_attr<256, 1>();
   if (e == cudaSuccess) e = set_tc_attr<128, 2>();
@@ -1043,6 +1168,9 @@ void ladiff_destroy(ladiff_handle* h) {
   for (auto& kv : h->raw) cudaFree(kv.second.dev);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int c = 0; c < MAX_CHAINS; ++c) {
+    if (h->aux[c]) cudaStreamDestroy(h->aux[c]);
+    if (h->ev_aux_fork[c]) cudaEventDestroy(h->ev_aux_fork[c]);
+    if (h->ev_aux_join[c]) cudaEventDestroy(h->ev_aux_join[c]);
     if (h->side[c]) cudaStreamDestroy(h->side[c]);
     if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
   }

@@ -16,12 +16,15 @@ struct LinArgs {
   int M_max;
   const int* M_dev;
   int N, K;
-  // fp32 operands (SIMT backend).  Two-source A: columns [0,K1) from A, [K1,K) from A2 (skip-merge, no concat)
+  // fp32 operands (SIMT backend).  Multi-source A: columns [0,K1) from A, [K1,K2) from A2, [K2,K) from A3 (skip merge /
+  // folded residual branches: no concat is ever materialised)
   const float* A;
   int lda;
   const float* A2;
   int lda2;
-  int K1;
+  const float* A3;
+  int lda3;
+  int K1, K2;
   const float* Wt;  // [K][ldw] fp32 (transposed nn.Linear weight)
   int ldw;
   // epilogue
@@ -40,7 +43,7 @@ struct LinArgs {
   int out_planes;       // 0 / 1 / 2 bf16 planes written
   int n_store;          // columns actually stored (<= N; 263 of 264..)
   // tensor-core backend
-  int a_plane_rows, a2_plane_rows, w_plane_rows;  // row offset of the lo plane inside each tensor map
+  int a_plane_rows, a2_plane_rows, a3_plane_rows, w_plane_rows;  // row offset of the lo plane inside each tensor map
   int dbg_flags;        // experiments (profiling only)
   long long* dbg;       // optional per-CTA clock stamps [ncta][16] (profiling builds of ladiff_linear_bench)
 };
@@ -95,7 +98,8 @@ __global__ void __launch_bounds__(256) k_linear_simt(const LinArgs p) {
       const long gr = row0 + r;
       const int gk = k0 + k;
       float v = 0.f;
-      if (gr < M) v = (gk < p.K1) ? p.A[gr * p.lda + gk] : p.A2[gr * p.lda2 + (gk - p.K1)];
+      if (gr < M)
+        v = (gk < p.K1) ? p.A[gr * p.lda + gk] : (gk < p.K2 ? p.A2[gr * p.lda2 + (gk - p.K1)] : p.A3[gr * p.lda3 + (gk - p.K2)]);
       As[r][k] = v;
     }
     for (int i = threadIdx.x; i < BK * 256; i += 256) {
@@ -174,13 +178,19 @@ struct TcCfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + W_BYTES);
   static constexpr int STAGES_FIT = (196 * 1024) / STAGE_BYTES;
+  // BN == 64 is the tile of the latency-bound denoiser links.  In plain bf16 mode its 4-stage ring is 96 KB, so two CTAs
+  // fit on an SM; the hi/lo split mode keeps the whole K = 256 operand set in flight (4 x 48 KB), one CTA per SM
+  // (a 2-stage ring measured slower: den_qkv 6.4 -> 7.9 us).
+  static constexpr int MIN_CTAS = (BN == 64 && NSPLIT == 1) ? 2 : 1;
   static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
   static constexpr int VEC_OFF = STAGES * STAGE_BYTES;
   static constexpr int VEC_BYTES = 1280 * 4;  // bias[256] | ln_g[256] | ln_b[256] | scale[256] | shift[256]
   static constexpr int BAR_OFF = VEC_OFF + VEC_BYTES;
-  static constexpr int STAT_BYTES = 4096;                    // cluster LayerNorm statistics (k_linear_tc_ln)
+  static constexpr int STAT_BYTES = 8192;                    // LayerNorm row statistics exchanged between epilogue warps / cluster CTAs
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + STAT_BYTES + 1024 /*align slack*/;
-  static constexpr int THREADS = 192;
+  static constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, each takes every other 32-column chunk
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;
   static constexpr int TILE_LD = 36;                         // floats; 144 B rows keep float4 accesses conflict-free
   static constexpr int TILE_BYTES = 32 * TILE_LD * 4;        // one warp-private 32x32 fp32 tile
   static_assert(8 * TILE_BYTES <= STAGES * STAGE_BYTES, "epilogue tiles must fit in the dead stage memory");
@@ -248,14 +258,12 @@ __device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs
     const bool two = p.out_planes > 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-      split_bf16(a[i].x, h0, l0);
-      split_bf16(a[i].y, h1, l1);
-      split_bf16(a[i].z, h2, l2);
-      split_bf16(a[i].w, h3, l3);
+      uint32_t h01, l01, h23, l23;
+      split2_bf16(a[i].x, a[i].y, h01, l01);
+      split2_bf16(a[i].z, a[i].w, h23, l23);
       if (i * 4 + (lane >> 3) < nvalid) {
-        *reinterpret_cast<uint2*>(dh + i * step) = make_uint2(pack2_bf16(h0, h1), pack2_bf16(h2, h3));
-        if (two) *reinterpret_cast<uint2*>(dl + i * step) = make_uint2(pack2_bf16(l0, l1), pack2_bf16(l2, l3));
+        *reinterpret_cast<uint2*>(dh + i * step) = make_uint2(h01, h23);
+        if (two) *reinterpret_cast<uint2*>(dl + i * step) = make_uint2(l01, l23);
       }
     }
   }
@@ -263,9 +271,9 @@ __device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs
 }
 
 template <int BN, int NSPLIT, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TcCfg<BN, NSPLIT>::THREADS, TcCfg<BN, NSPLIT>::MIN_CTAS)
 k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
+            const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
   using C = TcCfg<BN, NSPLIT>;
   constexpr int STAGES = C::STAGES;
   constexpr bool LN = (EPI == EPI_LN || EPI == EPI_LN_MOD_SILU);
@@ -276,6 +284,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int n0 = blockIdx.y * BN;
   const int nkb = p.K / C::BK;
   const int nkb1 = p.K1 / C::BK;
+  const int nkb2 = p.K2 / C::BK;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle; pointer arithmetic (no integer round trip) keeps the shared address space
@@ -303,10 +312,10 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   auto produce_a = [&](int kb) {
     const int s = kb % STAGES;
     uint8_t* st = smem + s * C::STAGE_BYTES;
-    const bool first = kb < nkb1;
-    const CUtensorMap* ma = first ? &tmA : &tmA2;
-    const int kcol = (first ? kb : kb - nkb1) * C::BK;
-    const int prow = first ? p.a_plane_rows : p.a2_plane_rows;
+    const int src = kb < nkb1 ? 0 : (kb < nkb2 ? 1 : 2);
+    const CUtensorMap* ma = src == 0 ? &tmA : (src == 1 ? &tmA2 : &tmA3);
+    const int kcol = (src == 0 ? kb : (src == 1 ? kb - nkb1 : kb - nkb2)) * C::BK;
+    const int prow = src == 0 ? p.a_plane_rows : (src == 1 ? p.a2_plane_rows : p.a3_plane_rows);
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(st + pl * C::A_BYTES, ma, &full[s], kcol, pl * prow + tile_m * C::BM);
   };
@@ -386,44 +395,49 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     __syncwarp();
   } else {
-    // ===== epilogue: 4 warps, thread <-> accumulator row =====
+    // ===== epilogue: 8 warps; thread <-> accumulator row, warp pair (w, w+4) shares a TMEM lane quarter and splits
+    // the 32-column chunks between them (chunk c belongs to half c & 1) =====
     // (1) while the mainloop runs: per-column vectors -> shared memory (read back as broadcast float4)
     const int et = threadIdx.x - 64;
-    for (int i = et; i < BN; i += 128) vec[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+    for (int i = et; i < BN; i += C::EPI_THREADS) vec[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
     if (LN) {
-      for (int i = et; i < 256; i += 128) {
+      for (int i = et; i < 256; i += C::EPI_THREADS) {
         vec[256 + i] = __ldg(p.ln_g + i);
         vec[512 + i] = __ldg(p.ln_b + i);
       }
     }
     tc::pdl_wait();  // everything below may belong to earlier grids (modulation table, residuals, outputs)
     if (EPI == EPI_LN_MOD_SILU) {
-      for (int i = et; i < 256; i += 128) {
+      for (int i = et; i < 256; i += C::EPI_THREADS) {
         vec[768 + i] = 1.f + p.mod[i];
         vec[1024 + i] = p.mod[256 + i];
       }
     }
-    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 2;  // 0..7
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int ch = ew >> 2;   // column half
     const int r = wq * 32 + lane;
     const long row = static_cast<long>(tile_m) * C::BM + r;
     const bool valid = row < M;
     const long row_base = static_cast<long>(tile_m) * C::BM + wq * 32;
     const int nvalid = static_cast<int>(min(32L, static_cast<long>(M) - row_base));  // may be <= 0
     const long drow = (valid && p.row_map) ? p.row_map[row] : row;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+    float* xs = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);  // [2 passes][2 halves][128 rows] LayerNorm partials
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
     // (2) accumulator ready
     tc::mbar_wait(accum_full, 0);
     tc::tc_fence_after();
     if (threadIdx.x == 64) STAMP(7);
-    float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + wq * C::TILE_BYTES);   // aliases dead stage memory
+    float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + ew * C::TILE_BYTES);   // aliases dead stage memory
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     const bool fast = (p.row_map == nullptr) && ((p.out.ld & 7) == 0);
     float v[32], t[32];
     if (LN) {
-      // BN == 256 == N: whole row in this thread.  3 passes over TMEM (exact two-pass variance).
+      // BN == 256 == N: the row lives in two threads (column halves).  3 passes over TMEM (exact two-pass variance),
+      // partial sums exchanged through shared memory.
       float s = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = ch; c < BN / 32; c += 2) {
         if (EPI == EPI_LN && p.res) warp_load_rows(tile, p.res, p.ldres, nullptr, row_base, nvalid, c * 32, lane, t);
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
@@ -439,11 +453,13 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int j = 0; j < 32; ++j) s += v[j];
         tc::tmem_st32(trow + c * 32, v);
       }
-      const float mean = s * (1.f / 256.f);
+      xs[ch * 128 + r] = s;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mean = (xs[r] + xs[128 + r]) * (1.f / 256.f);
       if (threadIdx.x == 64) STAMP(10);
       float q2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = ch; c < BN / 32; c += 2) {
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -451,10 +467,12 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           q2 += d * d;
         }
       }
-      const float rstd = 1.0f / sqrtf(q2 * (1.f / 256.f) + LD_EPS);
+      xs[256 + ch * 128 + r] = q2;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float rstd = 1.0f / sqrtf((xs[256 + r] + xs[384 + r]) * (1.f / 256.f) + LD_EPS);
       if (threadIdx.x == 64) STAMP(11);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = ch; c < BN / 32; c += 2) {
         if (EPI == EPI_LN && p.addv) warp_load_rows(tile, p.addv, p.ld_add, p.add_idx, row_base, nvalid, c * 32, lane, t);
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
@@ -485,7 +503,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = ch; c < BN / 32; c += 2) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.n_store) break;  // warp-uniform
         const bool full_chunk = fast && (col0 + 32 <= p.n_store);
@@ -507,7 +525,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (EPI == EPI_RELU) v[j] = fmaxf(v[j], 0.f);
-          else if (EPI == EPI_GELU) v[j] = gelu_erf(v[j]);
+          else if (EPI == EPI_GELU) v[j] = gelu_erf_fast(v[j]);
           else if (EPI == EPI_SILU) v[j] = silu(v[j]);
           else if (EPI == EPI_RES) v[j] += t[j];
         }
@@ -534,9 +552,9 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // distributed shared memory (two exact passes: sum -> mean, centred sum of squares -> rstd).  CL x more SMs work on
 // every 128-row tile than with a whole-row CTA, which is what the latency-bound denoiser loop (10 row tiles) needs.
 template <int CL, int NSPLIT, int EPI>
-__global__ void __cluster_dims__(1, CL, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(1, CL, 1) __launch_bounds__(TcCfg<256 / CL, NSPLIT>::THREADS, TcCfg<256 / CL, NSPLIT>::MIN_CTAS)
 k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
+               const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
   constexpr int BN = 256 / CL;
   static_assert(BN == 64 || BN == 128, "cluster split supports 2 or 4 CTAs");
   using C = TcCfg<BN, NSPLIT>;
@@ -550,6 +568,7 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n0 = static_cast<int>(rank) * BN;
   const int nkb = p.K / C::BK;
   const int nkb1 = p.K1 / C::BK;
+  const int nkb2 = p.K2 / C::BK;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -560,7 +579,7 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
   // row statistics exchanged across the cluster: [2 passes][CL ranks][128 rows]; lives after the epilogue tiles in the
   // (by then dead) stage memory is NOT possible -- peers write it while our mainloop may still run -> own region
-  float* stat = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // 2 * CL * 128 floats (<= 4 KB)
+  float* stat = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // 2 passes * 2 CL slots * 128 floats (<= 8 KB)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -576,10 +595,10 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto produce_a = [&](int kb) {
     const int s = kb % STAGES;
     uint8_t* st = smem + s * C::STAGE_BYTES;
-    const bool first = kb < nkb1;
-    const CUtensorMap* ma = first ? &tmA : &tmA2;
-    const int kcol = (first ? kb : kb - nkb1) * C::BK;
-    const int prow = first ? p.a_plane_rows : p.a2_plane_rows;
+    const int src = kb < nkb1 ? 0 : (kb < nkb2 ? 1 : 2);
+    const CUtensorMap* ma = src == 0 ? &tmA : (src == 1 ? &tmA2 : &tmA3);
+    const int kcol = (src == 0 ? kb : (src == 1 ? kb - nkb1 : kb - nkb2)) * C::BK;
+    const int prow = src == 0 ? p.a_plane_rows : (src == 1 ? p.a2_plane_rows : p.a3_plane_rows);
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(st + pl * C::A_BYTES, ma, &full[s], kcol, pl * prow + tile_m * C::BM);
   };
@@ -654,97 +673,105 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::cluster_sync();
   } else {
     const int et = threadIdx.x - 64;
-    for (int i = et; i < BN; i += 128) {
+    for (int i = et; i < BN; i += C::EPI_THREADS) {
       vec[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
       vec[256 + i] = __ldg(p.ln_g + n0 + i);
       vec[512 + i] = __ldg(p.ln_b + n0 + i);
     }
     tc::pdl_wait();
     if (EPI == EPI_LN_MOD_SILU) {
-      for (int i = et; i < BN; i += 128) {
+      for (int i = et; i < BN; i += C::EPI_THREADS) {
         vec[768 + i] = 1.f + p.mod[n0 + i];
         vec[1024 + i] = p.mod[256 + n0 + i];
       }
     }
+    const int ew = warp - 2;
     const int wq = warp & 3;
+    const int ch = ew >> 2;        // column half inside this CTA's BN columns: chunks ch, ch+2, ...
+    constexpr int NCHT = NCH / 2;  // chunks per thread
+    static_assert(NCH % 2 == 0, "two epilogue warps per lane quarter");
     const int r = wq * 32 + lane;
     const long row_base = static_cast<long>(tile_m) * C::BM + wq * 32;
     const int nvalid = static_cast<int>(min(32L, static_cast<long>(M) - row_base));
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     tc::mbar_wait(accum_full, 0);
     tc::tc_fence_after();
-    float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + wq * C::TILE_BYTES);
+    float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + ew * C::TILE_BYTES);
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    float v[NCH][32], t[32];
-    // pass A: v = acc + bias (+ residual); partial row sum over this CTA's columns
+    float v[NCHT][32], t[32];
+    // pass A: v = acc + bias (+ residual); partial row sum over this thread's columns
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
+    for (int ci = 0; ci < NCHT; ++ci) {
+      const int c = ch + 2 * ci;
       if (EPI == EPI_LN && p.res) warp_load_rows(tile, p.res, p.ldres, nullptr, row_base, nvalid, n0 + c * 32, lane, t);
-      tc::tmem_ld32(trow + c * 32, v[c]);
+      tc::tmem_ld32(trow + c * 32, v[ci]);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 b4 = *reinterpret_cast<const float4*>(vec + c * 32 + 4 * q);
-        v[c][4 * q] += b4.x; v[c][4 * q + 1] += b4.y; v[c][4 * q + 2] += b4.z; v[c][4 * q + 3] += b4.w;
+        v[ci][4 * q] += b4.x; v[ci][4 * q + 1] += b4.y; v[ci][4 * q + 2] += b4.z; v[ci][4 * q + 3] += b4.w;
       }
       if (EPI == EPI_LN && p.res) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[c][j] += t[j];
+        for (int j = 0; j < 32; ++j) v[ci][j] += t[j];
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) s += v[c][j];
+      for (int j = 0; j < 32; ++j) s += v[ci][j];
     }
+    // partials: [pass][2*CL slots = (rank, half)][128 rows], pushed into every CTA of the cluster
     const uint32_t stat_addr = tc::smem_u32(stat);
+    const uint32_t slot = rank * 2 + ch;
 #pragma unroll
-    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((0 * CL + rank) * 128 + r) * 4, k), s);
+    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((0 * 2 * CL + slot) * 128 + r) * 4, k), s);
     tc::cluster_sync();
     float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < CL; ++k) tot += stat[(0 * CL + k) * 128 + r];
+    for (int k = 0; k < 2 * CL; ++k) tot += stat[(0 * 2 * CL + k) * 128 + r];
     const float mean = tot * (1.f / 256.f);
     float q2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int ci = 0; ci < NCHT; ++ci)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float d = v[c][j] - mean;
+        const float d = v[ci][j] - mean;
         q2 += d * d;
       }
 #pragma unroll
-    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((1 * CL + rank) * 128 + r) * 4, k), q2);
+    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((1 * 2 * CL + slot) * 128 + r) * 4, k), q2);
     tc::cluster_sync();
     float qt = 0.f;
 #pragma unroll
-    for (int k = 0; k < CL; ++k) qt += stat[(1 * CL + k) * 128 + r];
+    for (int k = 0; k < 2 * CL; ++k) qt += stat[(1 * 2 * CL + k) * 128 + r];
     const float rstd = 1.0f / sqrtf(qt * (1.f / 256.f) + LD_EPS);
-    // pass C: normalise this CTA's columns and store
+    // pass C: normalise this thread's columns and store
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
+    for (int ci = 0; ci < NCHT; ++ci) {
+      const int c = ch + 2 * ci;
       if (EPI == EPI_LN && p.addv) warp_load_rows(tile, p.addv, p.ld_add, p.add_idx, row_base, nvalid, n0 + c * 32, lane, t);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 g4 = *reinterpret_cast<const float4*>(vec + 256 + c * 32 + 4 * q);
         const float4 b4 = *reinterpret_cast<const float4*>(vec + 512 + c * 32 + 4 * q);
-        v[c][4 * q] = (v[c][4 * q] - mean) * rstd * g4.x + b4.x;
-        v[c][4 * q + 1] = (v[c][4 * q + 1] - mean) * rstd * g4.y + b4.y;
-        v[c][4 * q + 2] = (v[c][4 * q + 2] - mean) * rstd * g4.z + b4.z;
-        v[c][4 * q + 3] = (v[c][4 * q + 3] - mean) * rstd * g4.w + b4.w;
+        v[ci][4 * q] = (v[ci][4 * q] - mean) * rstd * g4.x + b4.x;
+        v[ci][4 * q + 1] = (v[ci][4 * q + 1] - mean) * rstd * g4.y + b4.y;
+        v[ci][4 * q + 2] = (v[ci][4 * q + 2] - mean) * rstd * g4.z + b4.z;
+        v[ci][4 * q + 3] = (v[ci][4 * q + 3] - mean) * rstd * g4.w + b4.w;
       }
       if (EPI == EPI_LN_MOD_SILU) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 s4 = *reinterpret_cast<const float4*>(vec + 768 + c * 32 + 4 * q);
           const float4 h4 = *reinterpret_cast<const float4*>(vec + 1024 + c * 32 + 4 * q);
-          v[c][4 * q] = silu(v[c][4 * q] * s4.x + h4.x);
-          v[c][4 * q + 1] = silu(v[c][4 * q + 1] * s4.y + h4.y);
-          v[c][4 * q + 2] = silu(v[c][4 * q + 2] * s4.z + h4.z);
-          v[c][4 * q + 3] = silu(v[c][4 * q + 3] * s4.w + h4.w);
+          v[ci][4 * q] = silu(v[ci][4 * q] * s4.x + h4.x);
+          v[ci][4 * q + 1] = silu(v[ci][4 * q + 1] * s4.y + h4.y);
+          v[ci][4 * q + 2] = silu(v[ci][4 * q + 2] * s4.z + h4.z);
+          v[ci][4 * q + 3] = silu(v[ci][4 * q + 3] * s4.w + h4.w);
         }
       } else if (p.addv) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[c][j] += t[j];
+        for (int j = 0; j < 32; ++j) v[ci][j] += t[j];
       }
-      warp_store_rows(tile, p, row_base, nvalid, n0 + c * 32, lane, v[c]);
+      warp_store_rows(tile, p, row_base, nvalid, n0 + c * 32, lane, v[ci]);
     }
   }
   tc::tc_fence_before();
