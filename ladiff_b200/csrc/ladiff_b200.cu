@@ -94,7 +94,10 @@ struct Arena {
 };
 
 struct DenLayerW {
-  Weight qkv, out, ff1, ff2, ca_value, ca_out, gff1, gff2, ffn_out;
+  Weight qkv, ff1, ff2, ca_value, ca_out, gff1, gff2, ffn_out;
+  float* inx = nullptr;       // extended in-projection [1536,256]: q | k | 4 x (W_o[:,head] W_v[head])  (k_attn_ln)
+  float* inx_bias = nullptr;  // [1536]
+  float* out_bias = nullptr;  // out_proj.bias
   float *n1g, *n1b, *n2g, *n2b, *ca_tn_g, *ca_tn_b, *ca_sn_g, *ca_sn_b, *ffn_sn_g, *ffn_sn_b;
 };
 struct DecLayerW {
@@ -124,8 +127,7 @@ struct ladiff_handle {
   Weight den_skip[4], time1, time2, embproj, timekv_all, textkv_all, mod_all;
   // folded transitions: qkv of layer l+1 straight from (x3, s[, skip]) of layer l, and the skip merge
   // straight from (x3, s, skip) -- the residual GEMM and the skip Linear leave the critical path
-  Weight den_qkv_fold[NL];   // [l] for l = 1..8: K = 512 (l <= 4) or 768 (l >= 5)
-  Weight den_xb_fold[4];     // skip merge i: [S1 | S1 P | S2], K = 768
+  Weight den_qkv_fold[NL];   // [l] for l = 1..8: N = 1792 (q | k | 4 x v' | X), K = 512 (l <= 4) or 768 (l >= 5)
   float *den_fg = nullptr, *den_fb = nullptr, *den_pe = nullptr;
   // decoder
   DecLayerW dec[NL];
@@ -433,56 +435,52 @@ int pack_concat(H* h, cudaStream_t st, Weight* w, const std::vector<std::pair<co
 }
 
 // Folded layer transitions.  With Y_l = x3 + s P_l^T + p_l (StylizationBlock out-projection + residual,
-// mdiff_transformer.py:162,262) the next layer's in-projection is linear in (x3, s):
-//   l+1 <= 4:  qkv = x3 Wq^T + s (Wq P_l)^T + (Wq p_l + bq)
-//   l+1 >= 5:  X = Y_l S1^T + skip S2^T + sb  (cat + Linear(512->256), cross_attention.py:79-81), so
-//              qkv = x3 (Wq S1)^T + s (Wq S1 P_l)^T + skip (Wq S2)^T + (Wq (S1 p_l + sb) + bq)
-//              X   = x3 S1^T + s (S1 P_l)^T + skip S2^T + (S1 p_l + sb)
-// Products are formed once here (fp64 accumulate) and packed like any other weight; K sources are ordered (x3, s, skip).
+// mdiff_transformer.py:162,262) the next layer's input tokens X and their extended in-projection E (q | k | 4 x v', see
+// k_attn_ln) are linear in (x3, s[, skip]):
+//   l+1 <= 4:  X = Y_l                                  -> rows [ I | P_l ],              bias p_l
+//   l+1 >= 5:  X = Y_l S1^T + skip S2^T + sb            -> rows [ S1 | S1 P_l | S2 ],     bias S1 p_l + sb
+//              (cat + Linear(512->256), cross_attention.py:79-81)
+//   E-part  :  E X-rows, bias E (X-bias) + e
+// One GEMM per layer transition (N = 1536 + 256, K = 512 or 768; K sources ordered x3, s, skip) replaces the residual GEMM,
+// the skip Linear and the in-projection.  Products are formed once here (fp64 accumulate) and packed like any other weight.
 int fold_denoiser_transitions(H* h, cudaStream_t st) {
-  const int D = 256;
+  const int D = 256, NQ = DQ_LD, NX = DQX_LD;
   const std::string P = "denoiser.encoder.";
-  float *tmp = nullptr, *tb = nullptr, *m1 = nullptr, *v1 = nullptr;
-  CK(cudaMalloc(&tmp, 768ull * 768 * sizeof(float)));
-  CK(cudaMalloc(&tb, 768 * sizeof(float)));
-  CK(cudaMalloc(&m1, 768ull * 256 * sizeof(float)));
-  CK(cudaMalloc(&v1, 256 * sizeof(float)));
+  float *tmp = nullptr, *tb = nullptr;
+  CK(cudaMalloc(&tmp, static_cast<size_t>(NX) * 768 * sizeof(float)));
+  CK(cudaMalloc(&tb, NX * sizeof(float)));
   auto done = [&](int s) {
     cudaStreamSynchronize(st);
-    cudaFree(tmp); cudaFree(tb); cudaFree(m1); cudaFree(v1);
+    cudaFree(tmp);
+    cudaFree(tb);
     return s;
   };
   for (int l = 0; l + 1 < NL; ++l) {
-    const Raw *Pw, *Pb, *Wq, *bq;
+    const Raw *Pw, *Pb;
+    const float *E = h->den[l + 1].inx, *e = h->den[l + 1].inx_bias;  // extended in-projection of layer l+1
     int s_;
     if ((s_ = get_raw(h, P + block_name(l) + ".ffn.proj_out.out_layers.2.weight", {D, D}, &Pw)) != LADIFF_OK) return done(s_);
     if ((s_ = get_raw(h, P + block_name(l) + ".ffn.proj_out.out_layers.2.bias", {D}, &Pb)) != LADIFF_OK) return done(s_);
-    if ((s_ = get_raw(h, P + block_name(l + 1) + ".sa_block.self_attn.in_proj_weight", {3 * D, D}, &Wq)) != LADIFF_OK) return done(s_);
-    if ((s_ = get_raw(h, P + block_name(l + 1) + ".sa_block.self_attn.in_proj_bias", {3 * D}, &bq)) != LADIFF_OK) return done(s_);
+    const int K = (l + 1 <= 4) ? 2 * D : 3 * D;
+    float* X = tmp + static_cast<size_t>(NQ) * K;  // X-rows [256, K] live at rows [1536, 1792) of the packed matrix
+    float* xb = tb + NQ;
     if (l + 1 <= 4) {
-      const int K = 2 * D;
-      LAUNCH(k_copy2d, cdiv(768L * D, 256), 256, 0, st, Wq->dev, D, 768, D, tmp, K);
-      LAUNCH(k_fold_matmul, cdiv(768L * D, 256), 256, 0, st, Wq->dev, D, Pw->dev, D, 768, D, D, tmp + D, K);
-      LAUNCH(k_fold_matvec, cdiv(768, 256), 256, 0, st, Wq->dev, D, Pb->dev, bq->dev, 768, D, tb);
-      if ((s_ = pack_weight(h, *h->warena, st, &h->den_qkv_fold[l + 1], tmp, K, 768, K, tb)) != LADIFF_OK) return done(s_);
+      LAUNCH(k_set_identity, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, X, K, D);
+      LAUNCH(k_copy2d, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, Pw->dev, D, D, D, X + D, K);
+      CK(cudaMemcpyAsync(xb, Pb->dev, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-      const int i = l - 4, K = 3 * D;
+      const int i = l - 4;
       const Raw *S, *sb;
       if ((s_ = get_raw(h, P + "linear_blocks." + std::to_string(i) + ".weight", {D, 2 * D}, &S)) != LADIFF_OK) return done(s_);
       if ((s_ = get_raw(h, P + "linear_blocks." + std::to_string(i) + ".bias", {D}, &sb)) != LADIFF_OK) return done(s_);
-      // skip merge: [S1 | S1 P | S2], bias S1 p + sb
-      LAUNCH(k_copy2d, cdiv(256L * D, 256), 256, 0, st, S->dev, 2 * D, D, D, tmp, K);
-      LAUNCH(k_fold_matmul, cdiv(256L * D, 256), 256, 0, st, S->dev, 2 * D, Pw->dev, D, D, D, D, tmp + D, K);
-      LAUNCH(k_copy2d, cdiv(256L * D, 256), 256, 0, st, S->dev + D, 2 * D, D, D, tmp + 2 * D, K);
-      LAUNCH(k_fold_matvec, 1, 256, 0, st, S->dev, 2 * D, Pb->dev, sb->dev, D, D, v1);
-      if ((s_ = pack_weight(h, *h->warena, st, &h->den_xb_fold[i], tmp, K, D, K, v1)) != LADIFF_OK) return done(s_);
-      CK(cudaStreamSynchronize(st));
-      // in-projection of the merged tokens: Wq [S1 | S1 P | S2], bias Wq (S1 p + sb) + bq ; m1 = [S1 | S1 P | S2] (256 x 768) is tmp
-      CK(cudaMemcpyAsync(m1, tmp, 256ull * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      LAUNCH(k_fold_matmul, cdiv(768L * K, 256), 256, 0, st, Wq->dev, D, m1, K, 768, D, K, tmp, K);
-      LAUNCH(k_fold_matvec, cdiv(768, 256), 256, 0, st, Wq->dev, D, v1, bq->dev, 768, D, tb);
-      if ((s_ = pack_weight(h, *h->warena, st, &h->den_qkv_fold[l + 1], tmp, K, 768, K, tb)) != LADIFF_OK) return done(s_);
+      LAUNCH(k_copy2d, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, S->dev, 2 * D, D, D, X, K);
+      LAUNCH(k_fold_matmul, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, S->dev, 2 * D, Pw->dev, D, D, D, D, X + D, K);
+      LAUNCH(k_copy2d, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, S->dev + D, 2 * D, D, D, X + 2 * D, K);
+      LAUNCH(k_fold_matvec, 1, 256, 0, st, S->dev, 2 * D, Pb->dev, sb->dev, D, D, xb);
     }
+    LAUNCH(k_fold_matmul, cdiv(static_cast<long>(NQ) * K, 256), 256, 0, st, E, D, X, K, NQ, D, K, tmp, K);
+    LAUNCH(k_fold_matvec, cdiv(NQ, 256), 256, 0, st, E, D, xb, e, NQ, D, tb);
+    if ((s_ = pack_weight(h, *h->warena, st, &h->den_qkv_fold[l + 1], tmp, K, NX, K, tb)) != LADIFF_OK) return done(s_);
     CK(cudaStreamSynchronize(st));
   }
   return done(LADIFF_OK);
@@ -503,15 +501,34 @@ int finalize_denoiser(H* h, cudaStream_t st) {
   CKS(get_vec(h, P + "encoder.norm.weight", D, &h->den_fg));
   CKS(get_vec(h, P + "encoder.norm.bias", D, &h->den_fb));
   std::vector<std::pair<const Raw*, const Raw*>> inproj, mods;
+  std::vector<Raw> inx_raw(NL), inxb_raw(NL);
   for (int l = 0; l < NL; ++l) {
     const std::string L = P + "encoder." + block_name(l) + ".";
     DenLayerW& w = h->den[l];
     const Raw *ipw, *ipb;
     CKS(get_raw(h, L + "sa_block.self_attn.in_proj_weight", {3 * D, D}, &ipw));
     CKS(get_raw(h, L + "sa_block.self_attn.in_proj_bias", {3 * D}, &ipb));
-    CKS(pack_weight(h, *h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
-    inproj.push_back({ipw, ipb});
-    CKS(pack_linear(h, st, &w.out, L + "sa_block.self_attn.out_proj", D, D));
+    // extended in-projection: the out-projection is folded into the per-head values (see k_attn_ln)
+    const Raw *ow, *ob;
+    CKS(get_raw(h, L + "sa_block.self_attn.out_proj.weight", {D, D}, &ow));
+    CKS(get_raw(h, L + "sa_block.self_attn.out_proj.bias", {D}, &ob));
+    w.out_bias = ob->dev;
+    CK(h->warena->alloc(reinterpret_cast<void**>(&w.inx), static_cast<size_t>(DQ_LD) * D * sizeof(float)));
+    CK(h->warena->alloc(reinterpret_cast<void**>(&w.inx_bias), DQ_LD * sizeof(float)));
+    CK(cudaMemcpyAsync(w.inx, ipw->dev, 2ull * D * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(w.inx_bias, ipb->dev, 2 * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int hd = 0; hd < 4; ++hd) {
+      LAUNCH(k_fold_matmul, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, ow->dev + hd * 64, D, ipw->dev + (2 * D + hd * 64) * D, D, D, 64, D,
+             w.inx + (2 * D + hd * D) * D, D);
+      LAUNCH(k_fold_matvec, 1, 256, 0, st, ow->dev + hd * 64, D, ipb->dev + 2 * D + hd * 64, (const float*)nullptr, D, 64,
+             w.inx_bias + 2 * D + hd * D);
+    }
+    CKS(pack_weight(h, *h->warena, st, &w.qkv, w.inx, D, DQ_LD, D, w.inx_bias));
+    inx_raw[l].dev = w.inx;
+    inx_raw[l].shape = {DQ_LD, D};
+    inxb_raw[l].dev = w.inx_bias;
+    inxb_raw[l].shape = {DQ_LD};
+    inproj.push_back({&inx_raw[l], &inxb_raw[l]});
     CKS(pack_linear(h, st, &w.ff1, L + "sa_block.linear1", 1024, D));
     CKS(pack_linear(h, st, &w.ff2, L + "sa_block.linear2", D, 1024));
     CKS(get_vec(h, L + "sa_block.norm1.weight", D, &w.n1g));
@@ -545,7 +562,7 @@ int finalize_denoiser(H* h, cudaStream_t st) {
   for (int i = 0; i < 4; ++i) CKS(pack_linear(h, st, &h->den_skip[i], P + "encoder.linear_blocks." + std::to_string(i), D, 2 * D));
   CKS(fold_denoiser_transitions(h, st));
   // K/V rows of every layer's in_proj: the conditioning tokens are step- or prompt-invariant
-  CKS(pack_concat(h, st, &h->timekv_all, inproj, D, 2 * D, D));
+  CKS(pack_concat(h, st, &h->timekv_all, inproj, D, DC_LD, D));  // per layer: k | 4 x v' rows of the extended in-projection
   h->textkv_all = h->timekv_all;  // same matrix, applied to the text projection
   CKS(pack_concat(h, st, &h->mod_all, mods, 0, 2 * D, D));
   h->den_ready = true;
@@ -678,7 +695,7 @@ int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg, f
     CKS(alloc_act(h, ar, &p->t1, n, 256, f, tcm));
     CKS(alloc_act(h, ar, &p->temb, n, 256, true, tcm));
     CKS(alloc_act(h, ar, &p->st, n, 256, f, tcm));
-    CK(ar.alloc((void**)&p->timekv, static_cast<size_t>(n) * NL * 512 * sizeof(float)));
+    CK(ar.alloc((void**)&p->timekv, static_cast<size_t>(n) * NL * DC_LD * sizeof(float)));
     CK(ar.alloc((void**)&p->mod, static_cast<size_t>(n) * NL * 1024 * sizeof(float)));
   }
   if (ext_lat) {
@@ -691,7 +708,7 @@ int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg, f
   CKS(alloc_act(h, ar, &p->textp, S, 256, true, tcm));
   CKS(alloc_act(h, ar, &p->tn, S, 256, f, tcm));
   CKS(alloc_act(h, ar, &p->ca_a, n * S, 256, f, tcm));
-  CK(ar.alloc((void**)&p->textkv, static_cast<size_t>(S) * NL * 512 * sizeof(float)));
+  CK(ar.alloc((void**)&p->textkv, static_cast<size_t>(S) * NL * DC_LD * sizeof(float)));
   CK(ar.alloc((void**)&p->lny, static_cast<size_t>(NL) * S * 256 * sizeof(float)));
   CK(ar.alloc((void**)&p->delta, static_cast<size_t>(NL) * n * S * 256 * sizeof(float)));
   CKS(alloc_act(h, ar, &p->xin, R, 256, true, tcm));
@@ -703,7 +720,7 @@ int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg, f
   CKS(alloc_act(h, ar, &p->a, R, 256, f, tcm));
   CKS(alloc_act(h, ar, &p->hbuf, R, 1024, f, tcm));
   CKS(alloc_act(h, ar, &p->sbuf, R, 256, f, tcm));
-  CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * 768 * sizeof(float)));
+  CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * DQX_LD * sizeof(float)));
   return LADIFF_OK;
 }
 
@@ -717,7 +734,7 @@ int enqueue_time_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   c = LinCall(); c.A = &p->t1; c.W = &h->time2; c.M_max = n; c.out = p->temb.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   LAUNCHP(k_unary, cdiv(n * 256, 256), 256, 0, st, p->temb.act.f32, 256, n, 256, (int)U_SILU, p->st.act, pl);
-  c = LinCall(); c.A = &p->temb; c.W = &h->timekv_all; c.M_max = n; c.out = f32_only(p->timekv, NL * 512);
+  c = LinCall(); c.A = &p->temb; c.W = &h->timekv_all; c.M_max = n; c.out = f32_only(p->timekv, NL * DC_LD);
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->st; c.W = &h->mod_all; c.M_max = n; c.out = f32_only(p->mod, NL * 1024);
   CKS(launch_linear(h, st, mode, c));
@@ -734,7 +751,7 @@ int enqueue_text_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   LinCall c;
   c.A = &p->trelu; c.W = &h->embproj; c.M_max = S; c.out = p->textp.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
-  c = LinCall(); c.A = &p->textp; c.W = &h->textkv_all; c.M_max = S; c.out = f32_only(p->textkv, NL * 512);
+  c = LinCall(); c.A = &p->textp; c.W = &h->textkv_all; c.M_max = S; c.out = f32_only(p->textkv, NL * DC_LD);
   CKS(launch_linear(h, st, mode, c));
   for (int l = 0; l < NL; ++l) {
     const DenLayerW& w = h->den[l];
@@ -753,20 +770,16 @@ int enqueue_text_tables(H* h, DenoisePlan* p, cudaStream_t st) {
   return LADIFF_OK;
 }
 
-// One denoiser layer after its in-projection (p->qkv holds q|k|v of the layer input `in`): sa_block attention -> out-proj +
-// residual + LN -> ReLU FFN (+LN, + hoisted ca_block delta) -> GELU FFN -> Stylization prologue.  Leaves x3 (p->x3) and
-// s (p->sbuf); the layer output Y = x3 + s P^T + p is formed by the caller (folded into the next layer, see
-// fold_denoiser_transitions).  `join` (optional) is an event the residual `in` depends on (side branch).
-int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, const ActBuf& in, cudaEvent_t join) {
+// One denoiser layer after its in-projection (p->qkv rows hold q | k | 4 x v' [| X] of the layer input): fused sa_block
+// attention + out-proj + residual + LN (k_attn_ln) -> ReLU FFN (+LN, + hoisted ca_block delta) -> GELU FFN -> Stylization
+// prologue.  Leaves x3 (p->x3) and s (p->sbuf); the layer output Y = x3 + s P^T + p is never materialised except for the
+// last layer (it is folded into the next layer's in-projection, see fold_denoiser_transitions).
+int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, const float* res, int ld_res, const Act& xcopy) {
   const DenLayerW& w = h->den[l];
   const int mode = p->mode, pl = p->planes, R = p->Rmax, S = p->S, n = p->n;
   LinCall c;
-  LAUNCHP(k_attn_small<8>, cdiv(static_cast<long>(S) * 4 * 32, 256), 256, 0, st, p->qkv, p->off, S, p->textkv + l * 512, NL * 512,
-         p->timekv + static_cast<size_t>(step) * NL * 512 + l * 512, p->a.act, pl);
-  if (join) CK(cudaStreamWaitEvent(st, join, 0));
-  c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = in.act.f32;
-  c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl; c.no_pdl = join != nullptr;
-  CKS(launch_linear(h, st, mode, c));
+  LAUNCHP(k_attn_ln<8>, S, 128, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
+         p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl);
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = p->x1.act.f32;
@@ -784,24 +797,19 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
 }
 
 // SkipTransformerEncoder wiring (operator/cross_attention.py:69-85); the last layer's tokens end up in p->xa.
-// Critical path per layer: qkv (folded) -> attention -> out-proj+LN -> FFN1 -> FFN2+LN -> FFN1' -> FFN2'+Stylization.
-// The layer outputs Y_l (l < 4, kept for the skip connections) and the merged tokens X_{l+1} (l >= 4) are only needed as
-// the residual of the NEXT layer's out-proj, so their GEMMs run on a side stream (graph branch) meanwhile.
+// Six dependent launches per layer: in-projection (folded with the previous layer's output projection, residual and skip
+// merge) -> attention+LN -> FFN1 -> FFN2+LN -> FFN1' -> FFN2'+Stylization.
 int enqueue_den_tokens(H* h, DenoisePlan* p, cudaStream_t st, int step) {
-  const int mode = p->mode, pl = p->planes, R = p->Rmax;
-  const int ci = p->chain;
-  if (!h->aux[ci]) CK(cudaStreamCreateWithFlags(&h->aux[ci], cudaStreamNonBlocking));
-  if (!h->ev_aux_fork[ci]) CK(cudaEventCreateWithFlags(&h->ev_aux_fork[ci], cudaEventDisableTiming));
-  if (!h->ev_aux_join[ci]) CK(cudaEventCreateWithFlags(&h->ev_aux_join[ci], cudaEventDisableTiming));
-  cudaStream_t aux = h->aux[ci];
+  const int mode = p->mode, R = p->Rmax;
+  const Act none{nullptr, nullptr, 0, 0};
   LinCall c;
-  c.A = &p->xin; c.W = &h->den[0].qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
+  c.A = &p->xin; c.W = &h->den[0].qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, DQX_LD);
   CKS(launch_linear(h, st, mode, c));
-  const ActBuf* x = &p->xin;  // layer input (residual of the out-proj)
-  bool pending = false;       // side branch in flight
   for (int l = 0; l < NL; ++l) {
-    CKS(enqueue_den_layer(h, p, st, l, step, *x, pending ? h->ev_aux_join[ci] : nullptr));
-    pending = false;
+    // layer input X_l: the packed latents for l = 0, else the X columns of the folded in-projection; X_1..X_4 (= Y_0..Y_3)
+    // are also copied out (planes) for the U-Net skip connections of layers 8..5
+    const float* res = l == 0 ? p->xin.act.f32 : p->qkv + DQ_LD;
+    CKS(enqueue_den_layer(h, p, st, l, step, res, l == 0 ? 256 : DQX_LD, (l >= 1 && l <= 4) ? p->skip[l - 1].act : none));
     const DenLayerW& w = h->den[l];
     if (l == NL - 1) {  // last layer: Y_8 itself (input of encoder.norm in k_cfg_ddim / k_final_ln_out)
       c = LinCall(); c.A = &p->sbuf; c.W = &w.ffn_out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RES; c.res = p->x3.act.f32;
@@ -809,25 +817,8 @@ int enqueue_den_tokens(H* h, DenoisePlan* p, cudaStream_t st, int step) {
       CKS(launch_linear(h, st, mode, c));
       break;
     }
-    // ---- side branch: next layer's input tokens
-    CK(cudaEventRecord(h->ev_aux_fork[ci], st));
-    CK(cudaStreamWaitEvent(aux, h->ev_aux_fork[ci], 0));
-    if (l < 4) {
-      c = LinCall(); c.A = &p->sbuf; c.W = &w.ffn_out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RES; c.res = p->x3.act.f32;
-      c.out = p->skip[l].act; c.out_planes = pl; c.no_pdl = true;  // planes too: third K source of the mirrored layer's folds
-      CKS(launch_linear(h, aux, mode, c));
-      x = &p->skip[l];
-    } else {
-      c = LinCall(); c.A = &p->x3; c.A2 = &p->sbuf; c.A3 = &p->skip[7 - l]; c.W = &h->den_xb_fold[l - 4]; c.M_max = R; c.M_dev = p->R;
-      c.out = f32_only(p->xb.act.f32, 256); c.no_pdl = true;
-      CKS(launch_linear(h, aux, mode, c));
-      x = &p->xb;
-    }
-    CK(cudaEventRecord(h->ev_aux_join[ci], aux));
-    pending = true;
-    // ---- critical path: in-projection of layer l+1 straight from (x3, s[, skip])
     c = LinCall(); c.A = &p->x3; c.A2 = &p->sbuf; if (l >= 4) c.A3 = &p->skip[7 - l];
-    c.W = &h->den_qkv_fold[l + 1]; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
+    c.W = &h->den_qkv_fold[l + 1]; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, DQX_LD);
     CKS(launch_linear(h, st, mode, c));
   }
   return LADIFF_OK;
