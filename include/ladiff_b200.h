@@ -138,6 +138,11 @@ LADIFF_API int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const fl
 LADIFF_API int ladiff_linear_bench(ladiff_handle* h, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t mode,
                         int32_t iters, float* ms_per_launch_host, void* stream);
 
+/* Profiling hook (handle created with LADIFF_TRACE=1 in the environment): per fused-linear launch of the last
+ * ladiff_diffusion_reverse call, 8 x uint64 %globaltimer nanoseconds: [0] first CTA start, [1] last dependency wait returned,
+ * [2] last accumulator ready, [3] last CTA done.  Synchronises the device.  Returns the number of records. */
+LADIFF_API int ladiff_trace_read(ladiff_handle* h, uint64_t* out_host, int32_t max_launches, char* names_host, int32_t name_stride);
+
 /* Number of kernel launches (graph nodes included) enqueued by the last compute call on this handle. */
 LADIFF_API int64_t ladiff_last_launch_count(const ladiff_handle* h);
 

@@ -54,6 +54,8 @@ def load_library() -> C.CDLL:
     lib.ladiff_feats2joints.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.ladiff_linear_test.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.ladiff_linear_bench.argtypes = [vp, i32, i32, i32, i32, i32, i32, pf32, vp]
+    lib.ladiff_trace_read.argtypes = [vp, C.POINTER(C.c_uint64), i32, C.c_char_p, i32]
+    lib.ladiff_trace_read.restype = C.c_int
     lib.ladiff_last_launch_count.argtypes = [vp]
     lib.ladiff_last_launch_count.restype = i64
     for fn in ("ladiff_create", "ladiff_set_weight", "ladiff_finalize_weights", "ladiff_diffusion_reverse",
@@ -66,7 +68,8 @@ def load_library() -> C.CDLL:
 
 EXPORTS = ("ladiff_abi_version", "ladiff_create", "ladiff_destroy", "ladiff_last_error", "ladiff_set_weight",
            "ladiff_finalize_weights", "ladiff_diffusion_reverse", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step",
-           "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_last_launch_count")
+           "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_trace_read",
+           "ladiff_last_launch_count")
 
 
 def _i32(xs: Sequence[int]):
@@ -213,6 +216,17 @@ class Engine:
         out = torch.empty((M, N), device=self.device, dtype=torch.float32)
         self._check(self.lib.ladiff_linear_test(self._h, _ptr(A), _ptr(W), *[_ptr(t) for t in opt], M, N, K,
                                                 EPI[epilogue], mode, _ptr(out), _stream()), "linear_test")
+        return out
+
+    def trace_read(self, max_launches: int = 16384):
+        """[(name, start, wait_done, accum_ready, done)] in ns of the last diffusion_reverse (needs LADIFF_TRACE=1)."""
+        buf = (C.c_uint64 * (8 * max_launches))()
+        names = C.create_string_buffer(96 * max_launches)
+        n = self.lib.ladiff_trace_read(self._h, buf, max_launches, names, 96)
+        out = []
+        for i in range(n):
+            nm = names.raw[96 * i:96 * (i + 1)].split(b"\0", 1)[0].decode()
+            out.append((nm, int(buf[8 * i]), int(buf[8 * i + 1]), int(buf[8 * i + 2]), int(buf[8 * i + 3])))
         return out
 
     def linear_bench(self, M: int, N: int, K: int, epilogue: str = "bias", mode: int = MODE_BF16X3, iters: int = 20) -> float:

@@ -202,6 +202,12 @@ __global__ void k_attn_small(const float* __restrict__ qkv, const int* __restric
   }
 }
 
+__device__ __forceinline__ unsigned long long ktimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // sa_block attention with the out-projection folded into the values, + residual + LayerNorm (norm1) in one kernel.
 // The in-projection is extended at load time to  [ q(256) | k(256) | v'_0 .. v'_3 (4 x 256) | X(256) ]  with
 // v'_h = W_o[:, head h] (W_v[head h] x + b_v[head h])  (nn.MultiheadAttention out_proj is linear in the per-head values) and
@@ -214,61 +220,67 @@ __global__ void k_attn_small(const float* __restrict__ qkv, const int* __restric
 #define DQX_LD 1792   // ... | X : row pitch of the in-projection buffer
 #define DC_LD 1280    // conditioning-token table row per layer: k | 4 x v'
 template <int MAXT>
-__global__ void __launch_bounds__(128) k_attn_ln(const float* __restrict__ qkvx, const int* __restrict__ off, int S,
+__global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx, const int* __restrict__ off, int S,
                                                  const float* __restrict__ textkv, int ld_textkv,
                                                  const float* __restrict__ timekv, const float* __restrict__ res, int ld_res,
                                                  const float* __restrict__ bo, const float* __restrict__ g,
-                                                 const float* __restrict__ b, Act out, Act xcopy, int planes) {
+                                                 const float* __restrict__ b, Act out, Act xcopy, int planes,
+                                                 unsigned long long* trace) {
+  if (trace && threadIdx.x == 0) atomicMin(trace, ktimer());
   pdl_prologue();
+  if (trace && threadIdx.x == 0) atomicMin(trace + 1, ~ktimer());
   constexpr int NK = MAXT + 2;
   __shared__ float Qs[MAXT][256];
   __shared__ float Ks[NK][256];
   __shared__ float Ps[MAXT][4][NK];
-  __shared__ float red[2][4][MAXT];
+  __shared__ float red[2][8][MAXT];
   const int s = blockIdx.x;
   if (s >= S) return;
   const int r0 = off[s], m = min(off[s + 1] - r0, MAXT);
   if (m <= 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = 2 * threadIdx.x;
+  const int c = threadIdx.x;  // this thread's output column
   const float* tk = textkv + static_cast<long>(s) * ld_textkv;
-  // ---- all global loads up front
-  float2 v[4][NK], xr[MAXT];
+  // ---- all global loads up front (one memory round trip): k rows -> smem, v' and the residual -> registers, q -> smem
+  float v[4][NK], xr[MAXT];
 #pragma unroll
   for (int j = 0; j < NK; ++j) {
     const bool on = j < m || j >= MAXT;
-    const float* base = (j < MAXT) ? qkvx + static_cast<long>(r0 + j) * DQX_LD : (j == MAXT ? tk - 256 : timekv - 256);  // k at +256
-    const float2 kk = on ? *reinterpret_cast<const float2*>(base + 256 + c) : make_float2(0.f, 0.f);
-    *reinterpret_cast<float2*>(&Ks[j][c]) = kk;
+    // row base such that k sits at +256 and v'_h at +512 + 256 h for latent rows and conditioning-table rows alike
+    const float* base = (j < MAXT) ? qkvx + static_cast<long>(r0 + j) * DQX_LD : (j == MAXT ? tk - 256 : timekv - 256);
+    Ks[j][c] = on ? base[256 + c] : 0.f;
 #pragma unroll
-    for (int h = 0; h < 4; ++h) v[h][j] = on ? *reinterpret_cast<const float2*>(base + 512 + h * 256 + c) : make_float2(0.f, 0.f);
+    for (int h = 0; h < 4; ++h) v[h][j] = on ? base[512 + h * 256 + c] : 0.f;
   }
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
-    float2 q = make_float2(0.f, 0.f);
-    xr[i] = make_float2(0.f, 0.f);
+    float q = 0.f;
+    xr[i] = 0.f;
     if (i < m) {
-      q = *reinterpret_cast<const float2*>(qkvx + static_cast<long>(r0 + i) * DQX_LD + c);
-      xr[i] = *reinterpret_cast<const float2*>(res + static_cast<long>(r0 + i) * ld_res + c);
+      q = qkvx[static_cast<long>(r0 + i) * DQX_LD + c];
+      xr[i] = res[static_cast<long>(r0 + i) * ld_res + c];
     }
-    *reinterpret_cast<float2*>(&Qs[i][c]) = make_float2(q.x * 0.125f, q.y * 0.125f);  // 1/sqrt(64) on q, like nn.MultiheadAttention
+    Qs[i][c] = q * 0.125f;  // 1/sqrt(64) on q, like nn.MultiheadAttention
   }
   __syncthreads();
+  if (trace && threadIdx.x == 0) atomicMin(trace + 2, ~ktimer());
   // ---- scores: element e = (i, h, j); the 64-dim dot product walks d rotated by the lane to avoid bank conflicts
-  for (int e = threadIdx.x; e < m * 4 * NK; e += 128) {
+  for (int e = threadIdx.x; e < m * 4 * NK; e += 256) {
     const int j = e % NK, h = (e / NK) & 3, i = e / (4 * NK);
     float sc = -INFINITY;
     if (j < m || j >= MAXT) {
       const float* qp = &Qs[i][h * 64];
       const float* kp = &Ks[j][h * 64];
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < 64; d += 2) {
-        const int d0 = (d + lane) & 63, d1 = (d + 1 + lane) & 63;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; d += 4) {
+        const int d0 = (d + lane) & 63, d1 = (d + 1 + lane) & 63, d2 = (d + 2 + lane) & 63, d3 = (d + 3 + lane) & 63;
         a0 = fmaf(qp[d0], kp[d0], a0);
         a1 = fmaf(qp[d1], kp[d1], a1);
+        a2 = fmaf(qp[d2], kp[d2], a2);
+        a3 = fmaf(qp[d3], kp[d3], a3);
       }
-      sc = a0 + a1;
+      sc = (a0 + a1) + (a2 + a3);
     }
     Ps[i][h][j] = sc;
   }
@@ -289,67 +301,52 @@ __global__ void __launch_bounds__(128) k_attn_ln(const float* __restrict__ qkvx,
     for (int j = 0; j < NK; ++j) Ps[i][h][j] = pj[j] * inv;
   }
   __syncthreads();
-  // ---- out[i, c..c+1] = sum_h sum_j P[i][h][j] v'[h][j]
-  float2 acc[MAXT];
+  // ---- out[i, c] = sum_h sum_j P[i][h][j] v'[h][j][c]  + out_proj bias + residual
+  float acc[MAXT];
+  const float boc = bo[c];
 #pragma unroll
-  for (int i = 0; i < MAXT; ++i) acc[i] = make_float2(0.f, 0.f);
+  for (int i = 0; i < MAXT; ++i) acc[i] = boc + xr[i];
 #pragma unroll
   for (int h = 0; h < 4; ++h)
 #pragma unroll
     for (int j = 0; j < NK; ++j)
 #pragma unroll
-      for (int i = 0; i < MAXT; ++i) {
-        const float pw = (i < m) ? Ps[i][h][j] : 0.f;
-        acc[i].x = fmaf(pw, v[h][j].x, acc[i].x);
-        acc[i].y = fmaf(pw, v[h][j].y, acc[i].y);
-      }
-  // ---- + out_proj bias + residual, LayerNorm over the 256 columns (128 threads x 2)
-  const float2 bo2 = *reinterpret_cast<const float2*>(bo + c);
-  float part[MAXT];
+      for (int i = 0; i < MAXT; ++i) acc[i] = fmaf(Ps[i][h][j], v[h][j], acc[i]);  // rows >= m: P stays 0-initialised garbage-free (v = finite)
+  // ---- LayerNorm over the 256 columns (one per thread)
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
-    acc[i].x += bo2.x + xr[i].x;
-    acc[i].y += bo2.y + xr[i].y;
-    part[i] = (i < m) ? acc[i].x + acc[i].y : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < MAXT; ++i) {
-    const float w = warp_sum(part[i]);
+    const float w = warp_sum(i < m ? acc[i] : 0.f);
     if (lane == 0) red[0][warp][i] = w;
   }
   __syncthreads();
   float mean[MAXT];
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
-    mean[i] = (red[0][0][i] + red[0][1][i] + red[0][2][i] + red[0][3][i]) * (1.f / 256.f);
-    const float dx = acc[i].x - mean[i], dy = acc[i].y - mean[i];
-    const float w = warp_sum(i < m ? dx * dx + dy * dy : 0.f);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[0][w][i];
+    mean[i] = t * (1.f / 256.f);
+    const float dx = acc[i] - mean[i];
+    const float w = warp_sum(i < m ? dx * dx : 0.f);
     if (lane == 0) red[1][warp][i] = w;
   }
   __syncthreads();
-  const float2 g2 = *reinterpret_cast<const float2*>(g + c), b2 = *reinterpret_cast<const float2*>(b + c);
+  const float gc = g[c], bc = b[c];
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
     if (i < m) {
-      const float rstd = 1.0f / sqrtf((red[1][0][i] + red[1][1][i] + red[1][2][i] + red[1][3][i]) * (1.f / 256.f) + LD_EPS);
-      const float x = (acc[i].x - mean[i]) * rstd * g2.x + b2.x, y = (acc[i].y - mean[i]) * rstd * g2.y + b2.y;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[1][w][i];
+      const float rstd = 1.0f / sqrtf(t * (1.f / 256.f) + LD_EPS);
       const long o = static_cast<long>(r0 + i) * 256 + c;
-      if (out.f32) *reinterpret_cast<float2*>(out.f32 + o) = make_float2(x, y);
-      uint32_t hi, lo;
-      if (out.pl && planes > 0) {
-        split2_bf16(x, y, hi, lo);
-        *reinterpret_cast<uint32_t*>(out.pl + o) = hi;
-        if (planes > 1) *reinterpret_cast<uint32_t*>(out.pl + static_cast<long>(out.rows_alloc) * 256 + o) = lo;
-      }
+      act_store(out, planes, r0 + i, c, (acc[i] - mean[i]) * rstd * gc + bc);
       // the layer input itself, kept for the U-Net skip connections (third K source of the mirrored layer's in-projection)
-      if (xcopy.f32) *reinterpret_cast<float2*>(xcopy.f32 + o) = xr[i];
-      if (xcopy.pl && planes > 0) {
-        split2_bf16(xr[i].x, xr[i].y, hi, lo);
-        *reinterpret_cast<uint32_t*>(xcopy.pl + o) = hi;
-        if (planes > 1) *reinterpret_cast<uint32_t*>(xcopy.pl + static_cast<long>(xcopy.rows_alloc) * 256 + o) = lo;
-      }
+      if (xcopy.f32 || xcopy.pl) act_store(xcopy, planes, r0 + i, c, xr[i]);
+      (void)o;
     }
   }
+  if (trace && threadIdx.x == 0) atomicMin(trace + 3, ~ktimer());
 }
 
 // Final LayerNorm (encoder.norm) + CFG combine + DDIM step + next-step input, one warp per (prompt, latent row):

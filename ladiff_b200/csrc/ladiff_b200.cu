@@ -137,6 +137,10 @@ struct ladiff_handle {
   std::map<std::string, std::unique_ptr<ReversePlan>> rev_plans;
   std::map<std::string, std::unique_ptr<DecodePlan>> dec_plans;
   cudaStream_t cap_stream = nullptr;
+  // LADIFF_TRACE=1: per-launch %globaltimer records of the fused linears (ladiff_trace_read)
+  unsigned long long* trace = nullptr;
+  int trace_n = 0, trace_cap = 0;
+  std::vector<std::string> trace_names;
   cudaStream_t side[MAX_CHAINS] = {};       // forked streams of the chained reverse loop
   cudaStream_t aux[MAX_CHAINS] = {};        // per-chain side branch (off-critical-path residual / skip GEMMs)
   cudaEvent_t ev_aux_fork[MAX_CHAINS] = {}, ev_aux_join[MAX_CHAINS] = {};
@@ -311,6 +315,15 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
   a.out_planes = c.out_planes;
   a.n_store = c.n_store < 0 ? W.N : c.n_store;
   a.dbg = c.dbg;
+  a.trace = nullptr;
+  if (h->trace && h->trace_n < h->trace_cap) {
+    a.trace = h->trace + 8ull * h->trace_n;
+    char nm[96];
+    snprintf(nm, sizeof(nm), "lin M%d N%d K%d epi%d", c.M_max, W.N, W.K, c.epi);
+    if (static_cast<int>(h->trace_names.size()) <= h->trace_n) h->trace_names.resize(h->trace_n + 1);
+    h->trace_names[h->trace_n] = nm;
+    h->trace_n++;
+  }
   a.dbg_flags = getenv("LADIFF_DBG_FLAGS") ? atoi(getenv("LADIFF_DBG_FLAGS")) : 0;
   const bool ln = (c.epi == EPI_LN || c.epi == EPI_LN_MOD_SILU);
   if (ln && W.N != 256) return h->err.set(LADIFF_ERR_INVALID, "LayerNorm epilogue needs N == 256");
@@ -778,8 +791,18 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   const DenLayerW& w = h->den[l];
   const int mode = p->mode, pl = p->planes, R = p->Rmax, S = p->S, n = p->n;
   LinCall c;
-  LAUNCHP(k_attn_ln<8>, S, 128, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
-         p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl);
+  unsigned long long* tr = nullptr;
+  if (h->trace && h->trace_n < h->trace_cap) {
+    tr = h->trace + 8ull * h->trace_n;
+    if (static_cast<int>(h->trace_names.size()) <= h->trace_n) h->trace_names.resize(h->trace_n + 1);
+    h->trace_names[h->trace_n++] = "attn_ln M" + std::to_string(R) + " ";
+  }
+  if (p->T <= 5)
+    LAUNCHP(k_attn_ln<5>, S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
+           p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
+  else
+    LAUNCHP(k_attn_ln<8>, S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
+           p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = p->x1.act.f32;
@@ -1146,8 +1169,27 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
     g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     return LADIFF_ERR_CUDA;
   }
+  if (getenv("LADIFF_TRACE")) {
+    h->trace_cap = 16384;
+    if (cudaMalloc(&h->trace, 8ull * h->trace_cap * sizeof(unsigned long long)) != cudaSuccess) h->trace = nullptr;
+    if (h->trace) cudaMemset(h->trace, 0xFF, 8ull * h->trace_cap * sizeof(unsigned long long));
+  }
   *out = h.release();
   return LADIFF_OK;
+}
+
+int ladiff_trace_read(ladiff_handle* h, uint64_t* out_host, int32_t max_launches, char* names_host, int32_t name_stride) {
+  if (!h || !h->trace || !out_host) return 0;
+  cudaDeviceSynchronize();
+  int n = static_cast<int>(h->trace_names.size());
+  if (n > max_launches) n = max_launches;
+  cudaMemcpy(out_host, h->trace, 8ull * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < n; ++i) {
+    for (int s = 1; s < 4; ++s) out_host[8 * i + s] = ~out_host[8 * i + s];
+    if (names_host && name_stride > 0) snprintf(names_host + static_cast<size_t>(i) * name_stride, name_stride, "%s", h->trace_names[i].c_str());
+  }
+  cudaMemset(h->trace, 0xFF, 8ull * h->trace_cap * sizeof(unsigned long long));
+  return n;
 }
 
 void ladiff_destroy(ladiff_handle* h) {
@@ -1210,6 +1252,7 @@ int ladiff_diffusion_reverse(ladiff_handle* h, const float* text_emb_dev, const 
                              const float* c2_host, float guidance_scale, int32_t mode, float* z_out_dev, void* stream) {
   if (!h) return LADIFF_ERR_INVALID;
   h->launches = 0;
+  h->trace_n = 0;
   if (!h->den_ready) return h->err.set(LADIFF_ERR_STATE, "denoiser weights not finalised");
   CKS(check_mode(h, mode));
   if (!text_emb_dev || !lengths_host || !noise_dev || !timesteps_host || !c1_host || !c2_host || !z_out_dev || B < 1 || n_steps < 1)

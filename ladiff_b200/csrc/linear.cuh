@@ -46,7 +46,21 @@ struct LinArgs {
   int a_plane_rows, a2_plane_rows, a3_plane_rows, w_plane_rows;  // row offset of the lo plane inside each tensor map
   int dbg_flags;        // experiments (profiling only)
   long long* dbg;       // optional per-CTA clock stamps [ncta][16] (profiling builds of ladiff_linear_bench)
+  unsigned long long* trace;  // optional per-launch %globaltimer record (LADIFF_TRACE=1): [0] min CTA start, [1..3] ~max of
+                              // {dependency wait returned, accumulator ready, CTA done}
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// slot 0 keeps the minimum, slots >= 1 the maximum (stored complemented so that one memset(0xFF) initialises both)
+__device__ __forceinline__ void trace_mark(unsigned long long* tr, int slot) {
+  if (!tr) return;
+  const unsigned long long t = gtimer();
+  atomicMin(tr + slot, slot == 0 ? t : ~t);
+}
 
 // ------------------------------------------------------------------------------------------------
 // scalar epilogue shared by both backends (non-LN kinds)
@@ -299,6 +313,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   long long* dbg = p.dbg ? p.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 0) STAMP(0);
+  if (threadIdx.x == 0) trace_mark(p.trace, 0);
 
   // weights never depend on the previous grid, activations do: the W half of a stage may be requested before pdl_wait
   auto produce_w = [&](int kb) {
@@ -333,6 +348,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // the first ring pass needs no consumer hand-shake: start the loads before the CTA-wide setup barrier
       for (int kb = 0; kb < npre; ++kb) produce_w(kb);
       tc::pdl_wait();
+      trace_mark(p.trace, 1);
       for (int kb = 0; kb < npre; ++kb) produce_a(kb);
       STAMP(2);
     }
@@ -428,6 +444,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc::mbar_wait(accum_full, 0);
     tc::tc_fence_after();
     if (threadIdx.x == 64) STAMP(7);
+    if (threadIdx.x == 64) trace_mark(p.trace, 2);
     float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + ew * C::TILE_BYTES);   // aliases dead stage memory
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     const bool fast = (p.row_map == nullptr) && ((p.out.ld & 7) == 0);
@@ -539,6 +556,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(p.trace, 3);
   if (warp == 1) {
     __syncwarp();
     tc::tmem_dealloc(tmem_base, BN);
@@ -552,7 +570,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // distributed shared memory (two exact passes: sum -> mean, centred sum of squares -> rstd).  CL x more SMs work on
 // every 128-row tile than with a whole-row CTA, which is what the latency-bound denoiser loop (10 row tiles) needs.
 template <int CL, int NSPLIT, int EPI>
-__global__ void __cluster_dims__(1, CL, 1) __launch_bounds__(TcCfg<256 / CL, NSPLIT>::THREADS, TcCfg<256 / CL, NSPLIT>::MIN_CTAS)
+__global__ void __cluster_dims__(1, CL, 1) __launch_bounds__(TcCfg<256 / CL, NSPLIT>::THREADS, 1)
 k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
   constexpr int BN = 256 / CL;
@@ -565,6 +583,7 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc::pdl_launch_dependents();
   if (tile_m * C::BM >= M || (p.dbg_flags & 2)) return;  // cluster-uniform
   const uint32_t rank = tc::cluster_ctarank();
+  if (threadIdx.x == 0) trace_mark(p.trace, 0);
   const int n0 = static_cast<int>(rank) * BN;
   const int nkb = p.K / C::BK;
   const int nkb1 = p.K1 / C::BK;
@@ -615,6 +634,7 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::fence_proxy_async();
       for (int kb = 0; kb < npre; ++kb) produce_w(kb);
       tc::pdl_wait();
+      trace_mark(p.trace, 1);
       for (int kb = 0; kb < npre; ++kb) produce_a(kb);
     }
     __syncwarp();
@@ -637,7 +657,6 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-    tc::cluster_sync();
     tc::cluster_sync();
   } else if (warp == 1) {
     if (lane == 0) {
@@ -670,7 +689,6 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
     tc::cluster_sync();
-    tc::cluster_sync();
   } else {
     const int et = threadIdx.x - 64;
     for (int i = et; i < BN; i += C::EPI_THREADS) {
@@ -691,20 +709,47 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NCHT = NCH / 2;  // chunks per thread
     static_assert(NCH % 2 == 0, "two epilogue warps per lane quarter");
     const int r = wq * 32 + lane;
+    const long row = static_cast<long>(tile_m) * C::BM + r;
+    const bool valid = row < M;
     const long row_base = static_cast<long>(tile_m) * C::BM + wq * 32;
     const int nvalid = static_cast<int>(min(32L, static_cast<long>(M) - row_base));
+    // (1) while the mainloop runs: this thread's residual / broadcast-add values straight into registers (each thread reads
+    // its own 128-byte row segment; the lines stay in L1 across the 8 vector loads), so that nothing but the TMEM read and the
+    // statistics exchange is left on the critical path once the accumulator is ready
+    float t[NCHT][32], u[NCHT][32];
+#pragma unroll
+    for (int ci = 0; ci < NCHT; ++ci) {
+      const int c = ch + 2 * ci;
+      if (EPI == EPI_LN && p.res) {
+        const float4* src = reinterpret_cast<const float4*>(p.res + row * p.ldres + n0 + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 x = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[ci][4 * q] = x.x; t[ci][4 * q + 1] = x.y; t[ci][4 * q + 2] = x.z; t[ci][4 * q + 3] = x.w;
+        }
+      }
+      if (EPI == EPI_LN && p.addv) {
+        const long sr = valid ? static_cast<long>(__ldg(p.add_idx + row)) : 0;
+        const float4* src = reinterpret_cast<const float4*>(p.addv + sr * p.ld_add + n0 + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 x = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          u[ci][4 * q] = x.x; u[ci][4 * q + 1] = x.y; u[ci][4 * q + 2] = x.z; u[ci][4 * q + 3] = x.w;
+        }
+      }
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     tc::mbar_wait(accum_full, 0);
     tc::tc_fence_after();
+    if (threadIdx.x == 64) trace_mark(p.trace, 2);
     float (*tile)[36] = reinterpret_cast<float (*)[36]>(smem + ew * C::TILE_BYTES);
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    float v[NCHT][32], t[32];
-    // pass A: v = acc + bias (+ residual); partial row sum over this thread's columns
+    float v[NCHT][32];
+    // (2) v = acc + bias (+ residual); local mean and centred sum of squares over this thread's 32 * NCHT columns
     float s = 0.f;
 #pragma unroll
     for (int ci = 0; ci < NCHT; ++ci) {
       const int c = ch + 2 * ci;
-      if (EPI == EPI_LN && p.res) warp_load_rows(tile, p.res, p.ldres, nullptr, row_base, nvalid, n0 + c * 32, lane, t);
       tc::tmem_ld32(trow + c * 32, v[ci]);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -713,41 +758,46 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (EPI == EPI_LN && p.res) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[ci][j] += t[j];
+        for (int j = 0; j < 32; ++j) v[ci][j] += t[ci][j];
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) s += v[ci][j];
     }
-    // partials: [pass][2*CL slots = (rank, half)][128 rows], pushed into every CTA of the cluster
-    const uint32_t stat_addr = tc::smem_u32(stat);
-    const uint32_t slot = rank * 2 + ch;
-#pragma unroll
-    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((0 * 2 * CL + slot) * 128 + r) * 4, k), s);
-    tc::cluster_sync();
-    float tot = 0.f;
-#pragma unroll
-    for (int k = 0; k < 2 * CL; ++k) tot += stat[(0 * 2 * CL + k) * 128 + r];
-    const float mean = tot * (1.f / 256.f);
-    float q2 = 0.f;
+    constexpr float NLOC = 32.f * NCHT;
+    const float mloc = s * (1.f / NLOC);
+    float m2 = 0.f;
 #pragma unroll
     for (int ci = 0; ci < NCHT; ++ci)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float d = v[ci][j] - mean;
-        q2 += d * d;
+        const float d = v[ci][j] - mloc;
+        m2 += d * d;
       }
+    // (3) ONE exchange of (local mean, local M2) between the 2 * CL column groups of the row (Chan et al. pairwise
+    // combination: exact two-pass variance inside a group, group means combined afterwards), pushed into every CTA
+    const uint32_t stat_addr = tc::smem_u32(stat);
+    const uint32_t slot = rank * 2 + ch;
 #pragma unroll
-    for (int k = 0; k < CL; ++k) tc::st_cluster_f32(tc::mapa(stat_addr + ((1 * 2 * CL + slot) * 128 + r) * 4, k), q2);
+    for (int k = 0; k < CL; ++k) {
+      tc::st_cluster_f32(tc::mapa(stat_addr + ((0 * 2 * CL + slot) * 128 + r) * 4, k), mloc);
+      tc::st_cluster_f32(tc::mapa(stat_addr + ((1 * 2 * CL + slot) * 128 + r) * 4, k), m2);
+    }
     tc::cluster_sync();
-    float qt = 0.f;
+    float msum = 0.f, qsum = 0.f, mk[2 * CL];
 #pragma unroll
-    for (int k = 0; k < 2 * CL; ++k) qt += stat[(1 * 2 * CL + k) * 128 + r];
-    const float rstd = 1.0f / sqrtf(qt * (1.f / 256.f) + LD_EPS);
-    // pass C: normalise this thread's columns and store
+    for (int k = 0; k < 2 * CL; ++k) {
+      mk[k] = stat[(0 * 2 * CL + k) * 128 + r];
+      msum += mk[k];
+      qsum += stat[(1 * 2 * CL + k) * 128 + r];
+    }
+    const float mean = msum * (1.f / (2 * CL));
+#pragma unroll
+    for (int k = 0; k < 2 * CL; ++k) qsum += NLOC * (mk[k] - mean) * (mk[k] - mean);
+    const float rstd = 1.0f / sqrtf(qsum * (1.f / 256.f) + LD_EPS);
+    // (4) normalise this thread's columns and store
 #pragma unroll
     for (int ci = 0; ci < NCHT; ++ci) {
       const int c = ch + 2 * ci;
-      if (EPI == EPI_LN && p.addv) warp_load_rows(tile, p.addv, p.ld_add, p.add_idx, row_base, nvalid, n0 + c * 32, lane, t);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 g4 = *reinterpret_cast<const float4*>(vec + 256 + c * 32 + 4 * q);
@@ -769,13 +819,14 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else if (p.addv) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[ci][j] += t[j];
+        for (int j = 0; j < 32; ++j) v[ci][j] += u[ci][j];
       }
       warp_store_rows(tile, p, row_base, nvalid, n0 + c * 32, lane, v[ci]);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(p.trace, 3);
   if (warp == 1) {
     __syncwarp();
     tc::tmem_dealloc(tmem_base, BN);
