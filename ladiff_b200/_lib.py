@@ -54,6 +54,7 @@ def load_library() -> C.CDLL:
     lib.ladiff_feats2joints.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.ladiff_linear_test.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.ladiff_linear_bench.argtypes = [vp, i32, i32, i32, i32, i32, i32, pf32, vp]
+    lib.ladiff_ffn_test.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, vp, vp, pf32, vp]
     lib.ladiff_trace_read.argtypes = [vp, C.POINTER(C.c_uint64), i32, C.c_char_p, i32]
     lib.ladiff_trace_read.restype = C.c_int
     lib.ladiff_last_launch_count.argtypes = [vp]
@@ -68,7 +69,7 @@ def load_library() -> C.CDLL:
 
 EXPORTS = ("ladiff_abi_version", "ladiff_create", "ladiff_destroy", "ladiff_last_error", "ladiff_set_weight",
            "ladiff_finalize_weights", "ladiff_diffusion_reverse", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step",
-           "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_trace_read",
+           "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_ffn_test", "ladiff_trace_read",
            "ladiff_last_launch_count")
 
 
@@ -228,6 +229,16 @@ class Engine:
             nm = names.raw[96 * i:96 * (i + 1)].split(b"\0", 1)[0].decode()
             out.append((nm, int(buf[8 * i]), int(buf[8 * i + 1]), int(buf[8 * i + 2]), int(buf[8 * i + 3])))
         return out
+
+    def ffn_test(self, x: torch.Tensor, layer: int, mod: torch.Tensor, mode: int = MODE_BF16X3, fused: bool = True, iters: int = 0):
+        """(x3, s, ms) of the two feed-forward pairs of denoiser layer `layer` on rows x[M,256] (ladiff_ffn_test)"""
+        x = x.contiguous().float()
+        mod = mod.contiguous().float()
+        x3, s = torch.empty_like(x), torch.empty_like(x)
+        ms = C.c_float(0.0)
+        self._check(self.lib.ladiff_ffn_test(self._h, _ptr(x), x.shape[0], layer, _ptr(mod), mode, 1 if fused else 0, iters,
+                                             _ptr(x3), _ptr(s), C.byref(ms), _stream()), "ffn_test")
+        return x3, s, float(ms.value)
 
     def linear_bench(self, M: int, N: int, K: int, epilogue: str = "bias", mode: int = MODE_BF16X3, iters: int = 20) -> float:
         """average milliseconds per launch of one fused linear (device time, CUDA events)"""

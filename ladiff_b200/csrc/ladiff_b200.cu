@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "linear.cuh"
+#include "ffn_cluster.cuh"
 
 namespace {
 
@@ -36,7 +37,8 @@ struct Err {
 };
 thread_local std::string g_create_error;
 bool g_use_pdl = true;
-bool g_skip_pdl_once = false;  // next launch_pdl() uses a full dependency (kernel right after a cross-stream join)
+bool g_skip_pdl_once = false;
+long long* g_ffn_dbg = nullptr;  // ladiff_ffn_test with LADIFF_DBG_STAMPS=1  // next launch_pdl() uses a full dependency (kernel right after a cross-stream join)
 
 #define CK(expr)                                                                                      \
   do {                                                                                                \
@@ -359,6 +361,87 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
   if (bn == 256) return split ? launch_tc<256, 2>(h, st, c, a, tiles_m) : launch_tc<256, 1>(h, st, c, a, tiles_m);
   if (bn == 128) return split ? launch_tc<128, 2>(h, st, c, a, tiles_m) : launch_tc<128, 1>(h, st, c, a, tiles_m);
   return split ? launch_tc<64, 2>(h, st, c, a, tiles_m) : launch_tc<64, 1>(h, st, c, a, tiles_m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused FFN pairs on a cluster (ffn_cluster.cuh): up to two (W1, act, W2, LayerNorm-kind) pairs chained on one 128-row tile
+struct FfnPair {
+  const Weight* W1 = nullptr;
+  const Weight* W2 = nullptr;
+  int act = EPI_RELU, kind = EPI_LN;
+  const float *ln_g = nullptr, *ln_b = nullptr, *mod = nullptr;
+  Act out{nullptr, nullptr, 0, 0};
+};
+struct FfnCall {
+  const ActBuf* X = nullptr;
+  int M_max = 0;
+  const int* M_dev = nullptr;
+  int npairs = 0;
+  FfnPair pair[2];
+  const float* res = nullptr;   // pair 0
+  const float* addv = nullptr;  // pair 0
+  const int* add_idx = nullptr;
+  int ld_add = 256;
+  int out_planes = 0;
+  long long* dbg = nullptr;
+};
+
+bool ffn_cluster_enabled() { return getenv("LADIFF_NO_FFN_CLUSTER") == nullptr; }
+
+int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
+  if (mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "ffn cluster kernel is a tensor-core path");
+  if (c.npairs < 1 || c.npairs > 2 || !c.X || !c.X->has_map || c.X->act.ld != 256)
+    return h->err.set(LADIFF_ERR_INVALID, "ffn cluster: bad operands");
+  if (c.M_max <= 0) return LADIFF_OK;
+  FfnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M_max = c.M_max;
+  a.M_dev = c.M_dev;
+  a.npairs = c.npairs;
+  for (int i = 0; i < c.npairs; ++i) {
+    const FfnPair& q = c.pair[i];
+    if (!q.W1 || !q.W2 || q.W1->N != 1024 || q.W1->K != 256 || q.W2->N != 256 || q.W2->K != 1024)
+      return h->err.set(LADIFF_ERR_INVALID, "ffn cluster: pair %d must be 256 -> 1024 -> 256", i);
+    if (q.kind != EPI_LN && q.kind != EPI_LN_MOD_SILU) return h->err.set(LADIFF_ERR_INVALID, "ffn cluster: bad epilogue kind");
+    a.act[i] = q.act;
+    a.kind[i] = q.kind;
+    a.b1[i] = q.W1->bias;
+    a.b2[i] = q.W2->bias;
+    a.ln_g[i] = q.ln_g;
+    a.ln_b[i] = q.ln_b;
+    a.mod[i] = q.mod;
+    a.out[i] = q.out;
+    a.w1_plane_rows[i] = q.W1->n_pad;
+    a.w2_plane_rows[i] = q.W2->n_pad;
+  }
+  a.res = c.res;
+  a.addv = c.addv;
+  a.add_idx = c.add_idx;
+  a.ld_add = c.ld_add;
+  a.out_planes = c.out_planes;
+  a.x_plane_rows = c.X->act.rows_alloc;
+  a.dbg = c.dbg;
+  a.trace = nullptr;
+  if (h->trace && h->trace_n < h->trace_cap) {
+    a.trace = h->trace + 8ull * h->trace_n;
+    char nm[96];
+    snprintf(nm, sizeof(nm), "ffn_cluster M%d pairs%d", c.M_max, c.npairs);
+    if (static_cast<int>(h->trace_names.size()) <= h->trace_n) h->trace_names.resize(h->trace_n + 1);
+    h->trace_names[h->trace_n] = nm;
+    h->trace_n++;
+  }
+  const FfnPair& q0 = c.pair[0];
+  const FfnPair& q1 = c.pair[c.npairs - 1];
+  const int tiles_m = (c.M_max + 127) / 128;
+  dim3 grid(tiles_m, 8);
+  if (mode == LADIFF_MODE_BF16X3)
+    CK(launch_pdl(k_ffn_cluster<2>, grid, dim3(FfnCfg<2>::THREADS), FfnCfg<2>::SMEM_BYTES, st, c.X->map, q0.W1->map128, q0.W2->map256,
+                  q1.W1->map128, q1.W2->map256, a));
+  else
+    CK(launch_pdl(k_ffn_cluster<1>, grid, dim3(FfnCfg<1>::THREADS), FfnCfg<1>::SMEM_BYTES, st, c.X->map, q0.W1->map128, q0.W2->map256,
+                  q1.W1->map128, q1.W2->map256, a));
+  h->launches++;
+  return LADIFF_OK;
 }
 
 #define LAUNCH(kernel, grid, block, smem, st, ...)  \
@@ -803,6 +886,19 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   else
     LAUNCHP(k_attn_ln<8>, S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
+  if (mode != LADIFF_MODE_FP32 && ffn_cluster_enabled()) {
+    // both feed-forward pairs of the layer in ONE cluster kernel: x1 -> x3 (fp32 + planes) -> s (planes); h never leaves the SM
+    FfnCall f;
+    f.X = &p->x1; f.M_max = R; f.M_dev = p->R; f.npairs = 2; f.out_planes = pl;
+    f.res = p->x1.act.f32;
+    f.addv = p->delta + (static_cast<size_t>(l) * n + step) * S * 256; f.add_idx = p->row_seq; f.ld_add = 256;
+    f.pair[0].W1 = &w.ff1; f.pair[0].W2 = &w.ff2; f.pair[0].act = EPI_RELU; f.pair[0].kind = EPI_LN;
+    f.pair[0].ln_g = w.n2g; f.pair[0].ln_b = w.n2b; f.pair[0].out = p->x3.act;
+    f.pair[1].W1 = &w.gff1; f.pair[1].W2 = &w.gff2; f.pair[1].act = EPI_GELU; f.pair[1].kind = EPI_LN_MOD_SILU;
+    f.pair[1].ln_g = w.ffn_sn_g; f.pair[1].ln_b = w.ffn_sn_b;
+    f.pair[1].mod = p->mod + static_cast<size_t>(step) * NL * 1024 + l * 1024 + 512; f.pair[1].out = p->sbuf.act;
+    return launch_ffn_cluster(h, st, mode, f);
+  }
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = p->x1.act.f32;
@@ -1159,6 +1255,8 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(2));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<32>(1));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(1));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<2>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<1>::SMEM_BYTES);
   if (e == cudaSuccess) e = set_tc_attr<256, 2>();
   if (e == cudaSuccess) e = set_tc_attr<256, 1>();
   if (e == cudaSuccess) e = set_tc_attr<128, 2>();
@@ -1431,6 +1529,95 @@ int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const float* W_dev,
   c.out = f32_only(out_dev, N);
   CKS(launch_linear(h, st, mode, c));
   CK(cudaStreamSynchronize(st));
+  return LADIFF_OK;
+}
+
+// Test / measurement hook: the two feed-forward pairs of denoiser layer `layer` on M rows of x, either as ONE cluster
+// kernel (fused = 1) or as the four separate fused linears (fused = 0).  iters > 0 additionally times back-to-back launches.
+int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t layer, const float* mod_dev, int32_t mode,
+                    int32_t fused, int32_t iters, float* x3_out_dev, float* s_out_dev, float* ms_per_call_host, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  CKS(check_mode(h, mode));
+  if (!h->den_ready) return h->err.set(LADIFF_ERR_STATE, "denoiser weights not finalised");
+  if (!x_dev || !mod_dev || !x3_out_dev || !s_out_dev || M < 1 || layer < 0 || layer >= NL)
+    return h->err.set(LADIFF_ERR_INVALID, "ladiff_ffn_test: bad argument");
+  if (fused && mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "ladiff_ffn_test: the fused kernel is a tensor-core path");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DenLayerW& w = h->den[layer];
+  const int planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
+  const bool tcm = planes > 0;
+  Arena ar;
+  ActBuf x, x3, sb, hb;
+  CKS(alloc_act(h, ar, &x, M, 256, true, tcm));
+  CKS(alloc_act(h, ar, &x3, M, 256, true, tcm));
+  CKS(alloc_act(h, ar, &sb, M, 256, true, tcm));
+  CKS(alloc_act(h, ar, &hb, M, 1024, !tcm, tcm));
+  LAUNCHP(k_unary, cdiv(static_cast<long>(M) * 256, 256), 256, 0, st, x_dev, 256, M, 256, (int)U_COPY, x.act, planes);
+  auto run = [&]() -> int {
+    if (fused) {
+      FfnCall f;
+      f.X = &x; f.M_max = M; f.npairs = 2; f.out_planes = planes; f.res = x.act.f32;
+      f.pair[0].W1 = &w.ff1; f.pair[0].W2 = &w.ff2; f.pair[0].act = EPI_RELU; f.pair[0].kind = EPI_LN;
+      f.pair[0].ln_g = w.n2g; f.pair[0].ln_b = w.n2b; f.pair[0].out = x3.act;
+      f.pair[1].W1 = &w.gff1; f.pair[1].W2 = &w.gff2; f.pair[1].act = EPI_GELU; f.pair[1].kind = EPI_LN_MOD_SILU;
+      f.pair[1].ln_g = w.ffn_sn_g; f.pair[1].ln_b = w.ffn_sn_b; f.pair[1].mod = mod_dev; f.pair[1].out = sb.act;
+      f.dbg = g_ffn_dbg;
+      return launch_ffn_cluster(h, st, mode, f);
+    }
+    LinCall c;
+    c.A = &x; c.W = &w.ff1; c.M_max = M; c.epi = EPI_RELU; c.out = hb.act; c.out_planes = planes;
+    CKS(launch_linear(h, st, mode, c));
+    c = LinCall(); c.A = &hb; c.W = &w.ff2; c.M_max = M; c.epi = EPI_LN; c.res = x.act.f32; c.ln_g = w.n2g; c.ln_b = w.n2b;
+    c.out = x3.act; c.out_planes = planes;
+    CKS(launch_linear(h, st, mode, c));
+    c = LinCall(); c.A = &x3; c.W = &w.gff1; c.M_max = M; c.epi = EPI_GELU; c.out = hb.act; c.out_planes = planes;
+    CKS(launch_linear(h, st, mode, c));
+    c = LinCall(); c.A = &hb; c.W = &w.gff2; c.M_max = M; c.epi = EPI_LN_MOD_SILU; c.ln_g = w.ffn_sn_g; c.ln_b = w.ffn_sn_b; c.mod = mod_dev;
+    c.out = sb.act; c.out_planes = planes;
+    return launch_linear(h, st, mode, c);
+  };
+  CKS(run());
+  CK(cudaMemcpyAsync(x3_out_dev, x3.act.f32, static_cast<size_t>(M) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(s_out_dev, sb.act.f32, static_cast<size_t>(M) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (iters > 0 && ms_per_call_host) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) CKS(run());
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_call_host = ms / iters;
+  }
+  CK(cudaStreamSynchronize(st));
+  if (fused && getenv("LADIFF_DBG_STAMPS")) {
+    long long* dbg = nullptr;
+    const int ncta = ((M + 127) / 128) * 8;
+    CK(ar.alloc((void**)&dbg, ncta * 48 * sizeof(long long)));
+    CK(cudaMemsetAsync(dbg, 0, ncta * 48 * sizeof(long long), st));
+    g_ffn_dbg = dbg;
+    CKS(run());
+    g_ffn_dbg = nullptr;
+    CK(cudaStreamSynchronize(st));
+    std::vector<long long> hb(ncta * 48);
+    CK(cudaMemcpy(hb.data(), dbg, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int cta : {0, 3, ncta - 1}) {
+      const long long* d = hb.data() + cta * 48;
+      fprintf(stderr, "  cta %3d: wait %lld |", cta, d[1] - d[0]);
+      for (int pr = 0; pr < 2; ++pr) {
+        const long long* e = d + 20 * pr;
+        fprintf(stderr, " P%d mmaA0 %lld mmaA3 %lld w2full %lld h0 %lld h1 %lld | accA %lld hdone %lld accB %lld #1 %lld scat %lld #2 %lld red %lld #3 %lld st %lld #4 %lld |",
+                pr, e[2] - d[0], e[3] - d[0], e[4] - d[0], e[5] - d[0], e[6] - d[0], e[8] - d[0], e[9] - d[0], e[10] - d[0], e[11] - d[0],
+                e[12] - d[0], e[13] - d[0], e[14] - d[0], e[15] - d[0], e[16] - d[0], e[17] - d[0]);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
   return LADIFF_OK;
 }
 

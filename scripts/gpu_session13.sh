@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+LADIFF_DBG_STAMPS=1 timeout 120 python - <<'PY' 2>&1 | tee gpurun_out/s13_time.log
+import torch, sys
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+from ladiff_b200._lib import Engine, MODES
+from oracle import ladiff_oracle as O
+sd = O.make_state_dict(1234, 263, perturb=True)
+eng = Engine(nfeats=263)
+eng.set_weights({k: v.cuda() for k, v in O.sub(sd, "denoiser.").items()}, "denoiser.")
+eng.finalize(1)
+x = torch.randn(1280, 256).cuda(); mod = (0.3 * torch.randn(512)).cuda()
+for mode in ("bf16x3", "bf16"):
+    _, _, ms = eng.ffn_test(x, 3, mod, mode=MODES[mode], fused=True, iters=200)
+    print(f"{mode} fused: {ms*1e3:.2f} us per call (M=1280, back-to-back)")
+PY
