@@ -230,13 +230,15 @@ class Engine:
             out.append((nm, int(buf[8 * i]), int(buf[8 * i + 1]), int(buf[8 * i + 2]), int(buf[8 * i + 3])))
         return out
 
-    def ffn_test(self, x: torch.Tensor, layer: int, mod: torch.Tensor, mode: int = MODE_BF16X3, fused: bool = True, iters: int = 0):
-        """(x3, s, ms) of the two feed-forward pairs of denoiser layer `layer` on rows x[M,256] (ladiff_ffn_test)"""
+    def ffn_test(self, x: torch.Tensor, layer: int, mod: torch.Tensor, mode: int = MODE_BF16X3, fused=True, iters: int = 0):
+        """(x3, s, ms) of the two feed-forward pairs of denoiser layer `layer` on rows x[M,256] (ladiff_ffn_test).
+        fused: False = four separate fused linears, True = the fused kernel the plans would pick (token-group kernel
+        k_ffn_swap for M <= 1776, else the 128-row cluster kernel), 2 = force the 128-row cluster kernel."""
         x = x.contiguous().float()
         mod = mod.contiguous().float()
         x3, s = torch.empty_like(x), torch.empty_like(x)
         ms = C.c_float(0.0)
-        self._check(self.lib.ladiff_ffn_test(self._h, _ptr(x), x.shape[0], layer, _ptr(mod), mode, 1 if fused else 0, iters,
+        self._check(self.lib.ladiff_ffn_test(self._h, _ptr(x), x.shape[0], layer, _ptr(mod), mode, int(fused), iters,
                                              _ptr(x3), _ptr(s), C.byref(ms), _stream()), "ffn_test")
         return x3, s, float(ms.value)
 

@@ -40,6 +40,7 @@ struct FfnArgs {
   Act out[2];
   int out_planes;
   int x_plane_rows;      // row offset of the lo plane in the X tensor map
+  int rt;                // k_ffn_swap: tokens per cluster (16 / 32 / 48)
   int w1_plane_rows[2], w2_plane_rows[2];
   unsigned long long* trace;
   long long* dbg;        // optional per-CTA clock64 stamps [ncta][48] (ladiff_ffn_test with LADIFF_DBG_STAMPS=1)

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "linear.cuh"
 #include "ffn_cluster.cuh"
+#include "ffn_swap.cuh"
 
 namespace {
 
@@ -77,7 +78,8 @@ struct Weight {
 
 struct ActBuf {
   Act act{nullptr, nullptr, 0, 0};
-  CUtensorMap map;
+  CUtensorMap map;    // TMA box of 128 rows x 64 columns
+  CUtensorMap map16;  // box of 16 rows (k_ffn_swap token groups)
   bool has_map = false;
 };
 
@@ -189,6 +191,7 @@ int alloc_act(H* h, Arena& ar, ActBuf* b, int rows, int ld, bool f32, bool plane
     CK(ar.alloc(reinterpret_cast<void**>(&b->act.pl), 2 * n * sizeof(__nv_bfloat16)));
     CK(cudaMemset(b->act.pl, 0, 2 * n * sizeof(__nv_bfloat16)));
     CKS(make_map(h, &b->map, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 128));
+    CKS(make_map(h, &b->map16, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 16));
     b->has_map = true;
   }
   return LADIFF_OK;
@@ -384,9 +387,23 @@ struct FfnCall {
   int ld_add = 256;
   int out_planes = 0;
   long long* dbg = nullptr;
+  bool force_cluster = false;  // tests: the 128-row cluster kernel even where the swapped kernel would be chosen
 };
 
 bool ffn_cluster_enabled() { return getenv("LADIFF_NO_FFN_CLUSTER") == nullptr; }
+
+// Token-group size of the swapped kernel (ffn_swap.cuh): the smallest multiple of 16 whose clusters of 4 CTAs are all
+// co-resident on the 148 SMs; 0 = too many rows, use the 128-row cluster kernel.
+int ffn_swap_rt(int M_max) {
+  if (getenv("LADIFF_NO_FFN_SWAP")) return 0;
+  if (const char* e = getenv("LADIFF_FFN_RT")) {
+    const int v = atoi(e);
+    if (v == 16 || v == 32 || v == 48) return v;
+  }
+  for (int rt = 16; rt <= 48; rt += 16)
+    if (((M_max + rt - 1) / rt) * 4 <= 148) return rt;
+  return 0;
+}
 
 int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
   if (mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "ffn cluster kernel is a tensor-core path");
@@ -432,6 +449,20 @@ int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
   }
   const FfnPair& q0 = c.pair[0];
   const FfnPair& q1 = c.pair[c.npairs - 1];
+  const int rt = c.force_cluster ? 0 : ffn_swap_rt(c.M_max);
+  if (rt > 0) {
+    a.rt = rt;
+    if (a.trace) h->trace_names[h->trace_n - 1] = "ffn_swap M" + std::to_string(c.M_max) + " rt" + std::to_string(rt);
+    dim3 grid((c.M_max + rt - 1) / rt, 4);
+    if (mode == LADIFF_MODE_BF16X3)
+      CK(launch_pdl(k_ffn_swap<2>, grid, dim3(SwapCfg<2>::THREADS), SwapCfg<2>::smem_bytes(rt), st, c.X->map16, q0.W1->map128,
+                    q0.W2->map128, q1.W1->map128, q1.W2->map128, a));
+    else
+      CK(launch_pdl(k_ffn_swap<1>, grid, dim3(SwapCfg<1>::THREADS), SwapCfg<1>::smem_bytes(rt), st, c.X->map16, q0.W1->map128,
+                    q0.W2->map128, q1.W1->map128, q1.W2->map128, a));
+    h->launches++;
+    return LADIFF_OK;
+  }
   const int tiles_m = (c.M_max + 127) / 128;
   dim3 grid(tiles_m, 8);
   if (mode == LADIFF_MODE_BF16X3)
@@ -1257,6 +1288,8 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(1));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<2>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<1>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<1>::smem_bytes(48));
   if (e == cudaSuccess) e = set_tc_attr<256, 2>();
   if (e == cudaSuccess) e = set_tc_attr<256, 1>();
   if (e == cudaSuccess) e = set_tc_attr<128, 2>();
@@ -1563,6 +1596,7 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
       f.pair[1].W1 = &w.gff1; f.pair[1].W2 = &w.gff2; f.pair[1].act = EPI_GELU; f.pair[1].kind = EPI_LN_MOD_SILU;
       f.pair[1].ln_g = w.ffn_sn_g; f.pair[1].ln_b = w.ffn_sn_b; f.pair[1].mod = mod_dev; f.pair[1].out = sb.act;
       f.dbg = g_ffn_dbg;
+      f.force_cluster = fused == 2;
       return launch_ffn_cluster(h, st, mode, f);
     }
     LinCall c;
@@ -1597,24 +1631,23 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
   CK(cudaStreamSynchronize(st));
   if (fused && getenv("LADIFF_DBG_STAMPS")) {
     long long* dbg = nullptr;
-    const int ncta = ((M + 127) / 128) * 8;
-    CK(ar.alloc((void**)&dbg, ncta * 48 * sizeof(long long)));
-    CK(cudaMemsetAsync(dbg, 0, ncta * 48 * sizeof(long long), st));
+    const int rt = fused == 2 ? 0 : ffn_swap_rt(M);
+    const int ncta = rt > 0 ? ((M + rt - 1) / rt) * 4 : ((M + 127) / 128) * 8;
+    const int dstride = rt > 0 ? 128 : 48;
+    CK(ar.alloc((void**)&dbg, ncta * dstride * sizeof(long long)));
+    CK(cudaMemsetAsync(dbg, 0, ncta * dstride * sizeof(long long), st));
     g_ffn_dbg = dbg;
     CKS(run());
     g_ffn_dbg = nullptr;
     CK(cudaStreamSynchronize(st));
-    std::vector<long long> hb(ncta * 48);
+    std::vector<long long> hb(ncta * dstride);
     CK(cudaMemcpy(hb.data(), dbg, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    // clock64 stamps relative to the CTA start; slot meaning: see the FSTAMP / SSTAMP sites of the kernel (+20 per pair)
     for (int cta : {0, 3, ncta - 1}) {
-      const long long* d = hb.data() + cta * 48;
-      fprintf(stderr, "  cta %3d: wait %lld |", cta, d[1] - d[0]);
-      for (int pr = 0; pr < 2; ++pr) {
-        const long long* e = d + 20 * pr;
-        fprintf(stderr, " P%d mmaA0 %lld mmaA3 %lld w2full %lld h0 %lld h1 %lld | accA %lld hdone %lld accB %lld #1 %lld scat %lld #2 %lld red %lld #3 %lld st %lld #4 %lld |",
-                pr, e[2] - d[0], e[3] - d[0], e[4] - d[0], e[5] - d[0], e[6] - d[0], e[8] - d[0], e[9] - d[0], e[10] - d[0], e[11] - d[0],
-                e[12] - d[0], e[13] - d[0], e[14] - d[0], e[15] - d[0], e[16] - d[0], e[17] - d[0]);
-      }
+      const long long* d = hb.data() + cta * dstride;
+      fprintf(stderr, "  %s cta %3d:", rt > 0 ? "swap" : "cluster", cta);
+      for (int i = 1; i < dstride; ++i)
+        if (d[i]) fprintf(stderr, " [%d]%lld", i, d[i] - d[0]);
       fprintf(stderr, "\n");
     }
   }

@@ -309,7 +309,9 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* accum_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform and the TMA / MMA operands
+  // stay in uniform registers (a lane-0 branch makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT + R2UR waterfall loop)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   long long* dbg = p.dbg ? p.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 0) STAMP(0);
@@ -345,13 +347,17 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc::mbar_init(accum_full, 1);
       tc::fence_barrier_init();
       tc::fence_proxy_async();
-      // the first ring pass needs no consumer hand-shake: start the loads before the CTA-wide setup barrier
-      for (int kb = 0; kb < npre; ++kb) produce_w(kb);
-      tc::pdl_wait();
-      trace_mark(p.trace, 1);
-      for (int kb = 0; kb < npre; ++kb) produce_a(kb);
-      STAMP(2);
     }
+    __syncwarp();
+    // the first ring pass needs no consumer hand-shake: start the loads before the CTA-wide setup barrier
+    if (tc::elect_one())
+      for (int kb = 0; kb < npre; ++kb) produce_w(kb);
+    __syncwarp();
+    tc::pdl_wait();
+    if (lane == 0) trace_mark(p.trace, 1);
+    if (tc::elect_one())
+      for (int kb = 0; kb < npre; ++kb) produce_a(kb);
+    if (lane == 0) STAMP(2);
     __syncwarp();
   }
   if (warp == 1) {
@@ -365,29 +371,34 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) STAMP(1);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (remaining k-blocks) =====
-      for (int kb = npre; kb < nkb; ++kb) {
-        tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
+    // ===== TMA producer (remaining k-blocks): the whole warp runs the uniform loop, one elected lane issues =====
+    for (int kb = npre; kb < nkb; ++kb) {
+      tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
+      if (tc::elect_one()) {
         produce_w(kb);
         produce_a(kb);
       }
-      STAMP(3);
+      __syncwarp();
     }
+    if (lane == 0) STAMP(3);
     __syncwarp();  // reconverge before the CTA barrier (bar.sync counts per warp)
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (single thread) =====
+    {
+      // ===== MMA issuer (whole warp in the uniform loop, one elected lane issues) =====
       constexpr uint32_t idesc = tc::idesc_bf16_f32(C::BM, BN);
+      const uint32_t smem_u = tc::smem_u32(smem);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
-        if (kb == 0) STAMP(4);
-        if (kb == nkb - 1) STAMP(5);
-        const uint32_t sa = tc::smem_u32(smem + s * C::STAGE_BYTES);
+        if (lane == 0) {
+          if (kb == 0) STAMP(4);
+          if (kb == nkb - 1) STAMP(5);
+        }
+        const uint32_t sa = smem_u + s * C::STAGE_BYTES;
         const uint32_t sw = sa + NSPLIT * C::A_BYTES;
+        if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < C::BK / C::UMMA_K; ++kk) {
           const uint32_t koff = kk * C::UMMA_K * 2;  // bytes inside the 128B swizzle atom
@@ -405,9 +416,11 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         tc::mma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+        if (kb == nkb - 1) tc::mma_commit(accum_full);
+        }
+        __syncwarp();
       }
-      tc::mma_commit(accum_full);
-      STAMP(6);
+      if (lane == 0) STAMP(6);
     }
     __syncwarp();
   } else {
@@ -600,7 +613,9 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (by then dead) stage memory is NOT possible -- peers write it while our mainloop may still run -> own region
   float* stat = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // 2 passes * 2 CL slots * 128 floats (<= 8 KB)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform and the TMA / MMA operands
+  // stay in uniform registers (a lane-0 branch makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT + R2UR waterfall loop)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   // weights never depend on the previous grid, activations do: the W half of a stage may be requested before pdl_wait
   auto produce_w = [&](int kb) {
@@ -632,11 +647,15 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::mbar_init(accum_full, 1);
       tc::fence_barrier_init();
       tc::fence_proxy_async();
-      for (int kb = 0; kb < npre; ++kb) produce_w(kb);
-      tc::pdl_wait();
-      trace_mark(p.trace, 1);
-      for (int kb = 0; kb < npre; ++kb) produce_a(kb);
     }
+    __syncwarp();
+    if (tc::elect_one())
+      for (int kb = 0; kb < npre; ++kb) produce_w(kb);
+    __syncwarp();
+    tc::pdl_wait();
+    if (lane == 0) trace_mark(p.trace, 1);
+    if (tc::elect_one())
+      for (int kb = 0; kb < npre; ++kb) produce_a(kb);
     __syncwarp();
   }
   if (warp == 1) {
@@ -649,24 +668,27 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = npre; kb < nkb; ++kb) {
-        tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
+    for (int kb = npre; kb < nkb; ++kb) {
+      tc::mbar_wait(&empty[kb % STAGES], ((kb / STAGES) & 1) ^ 1);
+      if (tc::elect_one()) {
         produce_w(kb);
         produce_a(kb);
       }
+      __syncwarp();
     }
     __syncwarp();
     tc::cluster_sync();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = tc::idesc_bf16_f32(C::BM, BN);
+      const uint32_t smem_u = tc::smem_u32(smem);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         tc::mbar_wait(&full[s], (kb / STAGES) & 1);
         tc::tc_fence_after();
-        const uint32_t sa = tc::smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t sa = smem_u + s * C::STAGE_BYTES;
         const uint32_t sw = sa + NSPLIT * C::A_BYTES;
+        if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < C::BK / C::UMMA_K; ++kk) {
           const uint32_t koff = kk * C::UMMA_K * 2;
@@ -684,8 +706,10 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc::mma_commit(&empty[s]);
+        if (kb == nkb - 1) tc::mma_commit(accum_full);
+        }
+        __syncwarp();
       }
-      tc::mma_commit(accum_full);
     }
     __syncwarp();
     tc::cluster_sync();
