@@ -29,6 +29,10 @@ GUIDANCE = 7.5
 NFEATS = 263
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
+NCU_DRAM_BYTES = {"k_ffn_swap<2>": 7175680, "k_ffn_cluster<2>": 7165952}
+
+
 def lin(i, o):
     return 2.0 * i * o
 
@@ -272,6 +276,14 @@ def run_own(args):
             tf = 2.0 * M * N * K_ / (ms / 1e3) / 1e12
             kern[name] = {"M": M, "N": N, "K": K_, "us": ms * 1e3, "tflops": tf, "frac_of_bf16_burst": tf / peaks["bf16_burst"]}
         extra["kernels"] = kern
+        # the dominant kernel of the step (44 % of the launch-list time, profiles/r01e_launches_bf16x3.summary.txt): the fused
+        # feed-forward pairs of one denoiser layer (k_ffn_swap), timed alone with CUDA events inside the library on its stream
+        xk = torch.randn((2 * B * 5, 256), generator=g).to(dev)
+        mk = (0.3 * torch.randn((512,), generator=g)).to(dev)
+        _, _, ms_k = eng.ffn_test(xk, 4, mk, mode=mode, fused=True, iters=200)
+        fl_k = 2 * B * 5 * 2 * (lin(256, 1024) + lin(1024, 256))
+        extra["_dominant"] = {"kernel": "k_ffn_swap<2>" if args.mode == "bf16x3" else "k_ffn_swap<1>", "us_per_launch": ms_k * 1e3,
+                              "flops_per_launch": fl_k, "launches_per_step": 9 * STEPS_DDIM}
         # other precision modes, same workload
         for m in ("bf16", "bf16x3", "fp32"):
             if m == args.mode or (m == "fp32" and args.steps < 3):
@@ -322,10 +334,25 @@ def run_own(args):
         "gpu_launches": int(launches * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": None, "scope": "whole step",
                      "note": f"algorithmic FLOPs per step {flops / 1e12:.3f} T (denoiser {den_f / 1e12:.3f} + decoder {dec_f / 1e12:.3f}; SURVEY.md 8d) / step time; peak = bf16 sustained of {peaks['source']}"},
         "cpu_baseline": cpu,
     }
+    dom = extra.pop("_dominant", None)
+    if dom:
+        # roofline of the DOMINANT KERNEL (timed alone -> burst peak); the whole-step figure moves to roofline.path
+        ach_k = dom["flops_per_launch"] / (dom["us_per_launch"] * 1e-6) / 1e12
+        path = dict(out["roofline"])
+        out["roofline"] = {
+            "bound": "tensor", "achieved": ach_k, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": ach_k / peaks["bf16_burst"],
+            "traffic": NCU_DRAM_BYTES.get(dom["kernel"]), "kernel": dom["kernel"], "us_per_launch": dom["us_per_launch"],
+            "launches_per_step": dom["launches_per_step"],
+            "share_of_step": dom["us_per_launch"] * 1e-3 * dom["launches_per_step"] / ms_step,
+            "note": ("algorithmic FLOPs per launch = 1280 rows x 4 x lin(256,1024) (the two feed-forward pairs of one denoiser layer, "
+                     "SURVEY.md 8d rows 'sa ReLU-FFN' + 'GELU FFN'); bf16x3 issues 3x these on the tensor pipe; duration = CUDA events "
+                     f"around 200 back-to-back launches; peak = bf16 burst of {peaks['source']}; traffic = dram read+write per launch "
+                     "of the ncu --set full capture in profiles/r01e_ncu_full_layer_kernels.txt"),
+            "path": path}
     out.update(extra)
     print(json.dumps(out))
     if world > 1:

@@ -53,6 +53,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void st_cluster_v4u(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -87,7 +94,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   uint64_t* empty = bars + 4;               // [4]
   uint64_t* x_full = bars + 8;              // [4]
   uint64_t* acca = bars + 12;               // [2]  hidden M tile g accumulated
-  uint64_t* hfull = bars + 14;              // [2]  128 arrivals: h operand k-blocks 2g, 2g+1 written
+  uint64_t* hfull = bars + 14;              // [2]  256 arrivals: h operand k-blocks 2g, 2g+1 written
   uint64_t* accb = bars + 16;               // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
@@ -96,7 +103,10 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const int total = p.npairs * 16;          // weight stages: per pair 8 of W1 (g, kb) then 8 of W2 (g, kb)
 
   auto issue_load = [&](int j) {
-    const int slot = j & 3, pr = j >> 4, r = j & 15, ph = r >> 3, g = (r >> 2) & 1, kb = r & 3;
+    // stage r of a pair: r < 8 phase A (M tile g = r >> 2, k-block r & 3); r >= 8 phase B ordered by the availability of h:
+    // first every (out tile, k-block) that reads hidden M tile 0 (k-blocks 0, 1), then those reading tile 1 (k-blocks 2, 3)
+    const int slot = j & 3, pr = j >> 4, r = j & 15, ph = r >> 3;
+    const int g = ph ? (r >> 1) & 1 : (r >> 2) & 1, kb = ph ? ((r >> 2) & 1) * 2 + (r & 1) : r & 3;
     const CUtensorMap* m;
     int kcol, row, prow;
     if (ph == 0) {
@@ -117,6 +127,11 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 
   if (warp == 0) {
     if (lane == 0) {
+      tc::tma_prefetch_desc(&tmX);
+      tc::tma_prefetch_desc(&tmW1a);
+      tc::tma_prefetch_desc(&tmW2a);
+      tc::tma_prefetch_desc(&tmW1b);
+      tc::tma_prefetch_desc(&tmW2b);
       for (int i = 0; i < 4; ++i) {
         tc::mbar_init(&full[i], 1);
         tc::mbar_init(&empty[i], 1);
@@ -124,7 +139,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       }
       for (int i = 0; i < 2; ++i) {
         tc::mbar_init(&acca[i], 1);
-        tc::mbar_init(&hfull[i], 128);
+        tc::mbar_init(&hfull[i], C::EPI_WARPS * 32);
       }
       tc::mbar_init(accb, 1);
       tc::fence_barrier_init();
@@ -156,9 +171,8 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     if (tc::elect_one()) {
       for (int kb = 0; kb < 4; ++kb) {
         tc::mbar_expect_tx(&x_full[kb], NSPLIT * XT);
-        for (int pl = 0; pl < NSPLIT; ++pl)
-          for (int i = 0; i < rt / 16; ++i)
-            tc::tma_load_2d(xop + (kb * NSPLIT + pl) * XT + i * 2048, &tmX, &x_full[kb], kb * C::BK, pl * p.x_plane_rows + row0 + i * 16);
+        for (int pl = 0; pl < NSPLIT; ++pl)   // tmX has a box of rt rows
+          tc::tma_load_2d(xop + (kb * NSPLIT + pl) * XT, &tmX, &x_full[kb], kb * C::BK, pl * p.x_plane_rows + row0);
       }
     }
     __syncwarp();
@@ -183,10 +197,11 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     for (int pr = 0; pr < p.npairs; ++pr) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const int slot = r & 3, ph = r >> 3, g = (r >> 2) & 1, kb = r & 3;   // 16 stages per pair: slot = (16 pr + r) & 3
+        const int slot = r & 3, ph = r >> 3;   // 16 stages per pair: slot = (16 pr + r) & 3; stage order: see issue_load
+        const int g = ph ? (r >> 1) & 1 : (r >> 2) & 1, kb = ph ? ((r >> 2) & 1) * 2 + (r & 1) : r & 3;
         if (ph == 0) {
           if (pr == 0) tc::mbar_wait(&x_full[kb], 0);
-        } else if (g == 0) {
+        } else if ((r & 3) == 0) {
           tc::mbar_wait(&hfull[kb >> 1], pr & 1);
         }
         if (dbg && pr == 0 && lane == 0) dbg[48 + 2 * r] = clock64();
@@ -237,27 +252,33 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
     const int f = g * 128 + q * 32 + lane; // feature (hidden-slice feature in phase A, output feature in phase B)
     const uint32_t recv_local = tc::smem_u32(hr), xop_local = tc::smem_u32(xop);
-    const int c0 = lane * 8;               // owner phase: 8 features per lane
-    const float b1v0 = __ldg(p.b1[0] + rank * C::HS + f);
-    const float b1v1 = p.npairs > 1 ? __ldg(p.b1[1] + rank * C::HS + f) : 0.f;
+    // owner phase: one half-warp per owned token (tpc <= 12 tokens, 16 half-warps); lane l of the half-warp owns the features
+    // 4 l + 64 j .. + 3 (j = 0..3: one float4 per k-block -> conflict-free shared loads, 128-byte coalesced global stores)
+    const int otl = e * 2 + (lane >> 4), c0 = (lane & 15) * 4;
+    const bool own = otl < tpc;
+    const int otcl = static_cast<int>(rank) * tpc + otl;      // token inside the cluster's group
+    const long orow = static_cast<long>(row0) + otcl;
+    const bool ovalid = own && orow < M;
     tc::pdl_wait();
-    // owner-side operands of pair 0 (residual, hoisted ca_block delta) straight into registers while the mainloop runs
-    float rs[2][8], ad[2][8];
+    // owner-side operands straight into registers while the mainloop runs: va = residual (pair 0) / 1 + scale (pair 1),
+    // vb = hoisted ca_block delta (pair 0) / shift (pair 1)
+    float va[16], vb[16];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int k = 0; k < 16; ++k) va[k] = vb[k] = 0.f;
+    if (ovalid && p.kind[0] == EPI_LN) {
+      if (p.res) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) rs[u][k] = ad[u][k] = 0.f;
-      const int tl = e + 8 * u;
-      const long row = static_cast<long>(row0) + rank * tpc + tl;
-      if (tl < tpc && row < M && p.kind[0] == EPI_LN) {
-        if (p.res) {
-          const float4 a = *reinterpret_cast<const float4*>(p.res + row * C::D + c0), b = *reinterpret_cast<const float4*>(p.res + row * C::D + c0 + 4);
-          rs[u][0] = a.x; rs[u][1] = a.y; rs[u][2] = a.z; rs[u][3] = a.w; rs[u][4] = b.x; rs[u][5] = b.y; rs[u][6] = b.z; rs[u][7] = b.w;
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = *reinterpret_cast<const float4*>(p.res + orow * C::D + c0 + 64 * j);
+          va[4 * j] = a.x; va[4 * j + 1] = a.y; va[4 * j + 2] = a.z; va[4 * j + 3] = a.w;
         }
-        if (p.addv) {
-          const float* ap = p.addv + static_cast<long>(__ldg(p.add_idx + row)) * p.ld_add + c0;
-          const float4 a = *reinterpret_cast<const float4*>(ap), b = *reinterpret_cast<const float4*>(ap + 4);
-          ad[u][0] = a.x; ad[u][1] = a.y; ad[u][2] = a.z; ad[u][3] = a.w; ad[u][4] = b.x; ad[u][5] = b.y; ad[u][6] = b.z; ad[u][7] = b.w;
+      }
+      if (p.addv) {
+        const float* ap = p.addv + static_cast<long>(__ldg(p.add_idx + orow)) * p.ld_add + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + 64 * j);
+          vb[4 * j] = a.x; vb[4 * j + 1] = a.y; vb[4 * j + 2] = a.z; vb[4 * j + 3] = a.w;
         }
       }
     }
@@ -266,56 +287,58 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       const uint32_t par = pr & 1;
       const bool ln_res = p.kind[pr] == EPI_LN;
       const bool last = pr + 1 >= p.npairs;
-      // (1) hidden activation: accA^T -> + b1 -> act -> bf16 hi/lo planes of the phase-B operand (token-major, K-major swizzled)
-      tc::mbar_wait(&acca[g], par);
-      tc::tc_fence_after();
-      if (pr == 0 && e == 0 && lane == 0) trace_mark(p.trace, 2);
-      if (e == 0 && lane == 0) SSTAMP(8 + 20 * pr);
+      // (1) hidden activation: accA^T -> + b1 -> act -> bf16 hi/lo planes of the phase-B operand (token-major, K-major swizzled).
+      // All 8 warps work on M tile 0 (while the MMAs of tile 1 run), then on tile 1: warp (q, hsel) owns TMEM lanes 32 q .. and
+      // the token half hsel, so the part of this epilogue that is exposed after the last phase-A MMA is half a tile.
       {
-        const int kbh = f >> 6, within = f & 63;
-        uint8_t* hb = hr + (kbh * NSPLIT) * XT + (within & 7) * 2;
-        const int chunk = within >> 3;
+        const int hsel = e >> 2, tok0 = hsel * (rt >> 1), nch = rt >> 4;   // rt / 2 tokens in chunks of 8
         const bool relu = p.act[pr] == EPI_RELU;
-        const float b1 = pr ? b1v1 : b1v0;
-        for (int c = 0; c < rt / 16; ++c) {
-          float v[16];
-          tmem_ld16(tmem_base + tlane + g * rt + c * 16, v);
+#pragma unroll 1
+        for (int gt = 0; gt < 2; ++gt) {
+          const int fh = gt * 128 + q * 32 + lane;     // hidden feature inside this CTA's slice
+          const float b1 = __ldg(p.b1[pr] + rank * C::HS + fh);
+          tc::mbar_wait(&acca[gt], par);
+          tc::tc_fence_after();
+          if (pr == 0 && gt == 0 && e == 0 && lane == 0) trace_mark(p.trace, 2);
+          if (gt == 0 && e == 0 && lane == 0) SSTAMP(8 + 20 * pr);
+          const int kbh = fh >> 6, within = fh & 63, chunk = within >> 3;
+          uint8_t* hb = hr + (kbh * NSPLIT) * XT + (within & 7) * 2;
+          for (int c = 0; c < nch; ++c) {
+            float v[8];
+            const int t0 = tok0 + c * 8;               // multiple of 8: token t0 + k sits in row k of 8-row group t0 / 8
+            tmem_ld8(tmem_base + tlane + gt * rt + t0, v);
+            uint8_t* hrow = hb + (t0 >> 3) * 1024;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int t = c * 16 + k;
-            float x = v[k] + b1;
-            x = relu ? fmaxf(x, 0.f) : gelu_erf_fast(x);
-            __nv_bfloat16 hi, lo;
-            split_bf16(x, hi, lo);
-            const int off = (t >> 3) * 1024 + (t & 7) * 128 + ((chunk ^ (t & 7)) << 4);
-            *reinterpret_cast<__nv_bfloat16*>(hb + off) = hi;
-            if (NSPLIT == 2) *reinterpret_cast<__nv_bfloat16*>(hb + XT + off) = lo;
+            for (int k = 0; k < 8; ++k) {
+              float x = v[k] + b1;
+              x = relu ? fmaxf(x, 0.f) : gelu_erf_fast(x);
+              __nv_bfloat16 hi, lo;
+              split_bf16(x, hi, lo);
+              const int off = k * 128 + ((chunk ^ k) << 4);
+              *reinterpret_cast<__nv_bfloat16*>(hrow + off) = hi;
+              if (NSPLIT == 2) *reinterpret_cast<__nv_bfloat16*>(hrow + XT + off) = lo;
+            }
           }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&hfull[gt]);
         }
-        tc::fence_proxy_async();
-        tc::mbar_arrive(&hfull[g]);
       }
       if (e == 0 && lane == 0) SSTAMP(9 + 20 * pr);
-      // per-feature vectors of the owner phase (weights: L2 hits), loaded while phase B runs
-      float b2v[8], gv[8], bv[8], m1[8], m2[8];
-      {
-        const float4 *pb2 = reinterpret_cast<const float4*>(p.b2[pr] + c0), *pg = reinterpret_cast<const float4*>(p.ln_g[pr] + c0),
-                     *pb = reinterpret_cast<const float4*>(p.ln_b[pr] + c0);
+      // per-feature vectors of the owner phase (weights: L2 hits), requested while phase B runs
+      float4 b2v[4], gv[4], bv[4];
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          const float4 a = __ldg(pb2 + hlf), b = __ldg(pg + hlf), c = __ldg(pb + hlf);
-          b2v[4 * hlf] = a.x; b2v[4 * hlf + 1] = a.y; b2v[4 * hlf + 2] = a.z; b2v[4 * hlf + 3] = a.w;
-          gv[4 * hlf] = b.x; gv[4 * hlf + 1] = b.y; gv[4 * hlf + 2] = b.z; gv[4 * hlf + 3] = b.w;
-          bv[4 * hlf] = c.x; bv[4 * hlf + 1] = c.y; bv[4 * hlf + 2] = c.z; bv[4 * hlf + 3] = c.w;
-        }
+      for (int j = 0; j < 4; ++j) {
+        b2v[j] = __ldg(reinterpret_cast<const float4*>(p.b2[pr] + c0 + 64 * j));
+        gv[j] = __ldg(reinterpret_cast<const float4*>(p.ln_g[pr] + c0 + 64 * j));
+        bv[j] = __ldg(reinterpret_cast<const float4*>(p.ln_b[pr] + c0 + 64 * j));
+      }
+      if (!ln_res) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m1[k] = m2[k] = 0.f;
-        if (!ln_res) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            m1[k] = 1.f + p.mod[pr][c0 + k];
-            m2[k] = p.mod[pr][C::D + c0 + k];
-          }
+        for (int j = 0; j < 4; ++j) {
+          const float4 s4 = *reinterpret_cast<const float4*>(p.mod[pr] + c0 + 64 * j);
+          const float4 h4 = *reinterpret_cast<const float4*>(p.mod[pr] + C::D + c0 + 64 * j);
+          va[4 * j] = 1.f + s4.x; va[4 * j + 1] = 1.f + s4.y; va[4 * j + 2] = 1.f + s4.z; va[4 * j + 3] = 1.f + s4.w;
+          vb[4 * j] = h4.x; vb[4 * j + 1] = h4.y; vb[4 * j + 2] = h4.z; vb[4 * j + 3] = h4.w;
         }
       }
       // (2) partial outputs -> owners (tokens tpc*k .. of the group belong to CTA k); 32 lanes = 128 contiguous bytes
@@ -346,71 +369,93 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       if (e == 0 && lane == 0) SSTAMP(12 + 20 * pr);
       tc::cluster_sync();  // #2: all partials have landed
       if (e == 0 && lane == 0) SSTAMP(13 + 20 * pr);
-      // (3) owner: fixed-order sum of the 4 partials + bias (+ residual), LayerNorm over the token (one warp), epilogue math
-      const Act& o = p.out[pr];
+      // (3) owner: fixed-order sum of the 4 partials + bias (+ residual), LayerNorm over the token (16 lanes), epilogue math
+      {
+        const Act& o = p.out[pr];
+        float y[16];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int tl = e + 8 * u;
-        if (tl < tpc) {
-        const int tcl = static_cast<int>(rank) * tpc + tl;  // token inside the cluster's group
-        const long row = static_cast<long>(row0) + tcl;
-        const bool valid = row < M;
-        float y[8];
+        for (int k = 0; k < 16; ++k) y[k] = 0.f;
+        if (own) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) y[k] = 0.f;
+          for (int s4 = 0; s4 < C::CL; ++s4) {
+            const float* rp = reinterpret_cast<const float*>(hr) + (s4 * tpc + otl) * C::D + c0;
 #pragma unroll
-        for (int s = 0; s < C::CL; ++s) {
-          const float* rp = reinterpret_cast<const float*>(hr) + (s * tpc + tl) * C::D + c0;
-          const float4 a = *reinterpret_cast<const float4*>(rp), b = *reinterpret_cast<const float4*>(rp + 4);
-          y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; y[4] += b.x; y[5] += b.y; y[6] += b.z; y[7] += b.w;
+            for (int j = 0; j < 4; ++j) {
+              const float4 a = *reinterpret_cast<const float4*>(rp + 64 * j);
+              y[4 * j] += a.x; y[4 * j + 1] += a.y; y[4 * j + 2] += a.z; y[4 * j + 3] += a.w;
+            }
+          }
         }
+        if (e == 0 && lane == 0) SSTAMP(14 + 20 * pr);
         float sm = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          y[k] += b2v[k] + (pr == 0 ? rs[u][k] : 0.f);
+        for (int j = 0; j < 4; ++j) {
+          y[4 * j] += b2v[j].x; y[4 * j + 1] += b2v[j].y; y[4 * j + 2] += b2v[j].z; y[4 * j + 3] += b2v[j].w;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (ln_res) y[k] += va[k];
           sm += y[k];
         }
-        const float mean = warp_sum(sm) * (1.f / 256.f);
+#pragma unroll
+        for (int ofs = 8; ofs > 0; ofs >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, ofs);
+        const float mean = sm * (1.f / 256.f);
         float q2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 16; ++k) {
           const float dd = y[k] - mean;
           q2 += dd * dd;
         }
-        const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.f / 256.f) + LD_EPS);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          y[k] = (y[k] - mean) * rstd * gv[k] + bv[k];
-          if (ln_res) y[k] += (pr == 0 ? ad[u][k] : 0.f);
-          else y[k] = silu(y[k] * m1[k] + m2[k]);
+        for (int ofs = 8; ofs > 0; ofs >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, ofs);
+        const float rstd = 1.0f / sqrtf(q2 * (1.f / 256.f) + LD_EPS);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          y[4 * j] = (y[4 * j] - mean) * rstd * gv[j].x + bv[j].x;
+          y[4 * j + 1] = (y[4 * j + 1] - mean) * rstd * gv[j].y + bv[j].y;
+          y[4 * j + 2] = (y[4 * j + 2] - mean) * rstd * gv[j].z + bv[j].z;
+          y[4 * j + 3] = (y[4 * j + 3] - mean) * rstd * gv[j].w + bv[j].w;
         }
-        uint4 hi4, lo4;
-        split2_bf16(y[0], y[1], hi4.x, lo4.x);
-        split2_bf16(y[2], y[3], hi4.y, lo4.y);
-        split2_bf16(y[4], y[5], hi4.z, lo4.z);
-        split2_bf16(y[6], y[7], hi4.w, lo4.w);
-        if (valid) {
-          if (o.f32) {
-            *reinterpret_cast<float4*>(o.f32 + row * o.ld + c0) = make_float4(y[0], y[1], y[2], y[3]);
-            *reinterpret_cast<float4*>(o.f32 + row * o.ld + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
-          }
-          if (o.pl && p.out_planes > 0) {
-            __nv_bfloat16* dh = o.pl + row * o.ld + c0;
-            *reinterpret_cast<uint4*>(dh) = hi4;
-            if (p.out_planes > 1) *reinterpret_cast<uint4*>(dh + static_cast<long>(o.rows_alloc) * o.ld) = lo4;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (ln_res) {
+            y[k] += vb[k];
+          } else {  // SiLU with the fast exponential / reciprocal (<= 2 ulp each; the bf16x3 products are ~1e-5 relative)
+            const float z = y[k] * va[k] + vb[k];
+            y[k] = __fdividef(z, 1.0f + __expf(-z));
           }
         }
-        if (!last) {
-          // next X operand into every CTA of the cluster: features c0..c0+7 = one 16-byte swizzle chunk of k-block c0 / 64
-          const int kb = c0 >> 6, chunk = (c0 & 63) >> 3;
-          const uint32_t off = (kb * NSPLIT) * XT + (tcl >> 3) * 1024 + (tcl & 7) * 128 + ((chunk ^ (tcl & 7)) << 4);
+        if (e == 0 && lane == 0) SSTAMP(15 + 20 * pr);
+        uint2 hi2[4], lo2[4];   // per k-block j: features c0 + 64 j .. + 3
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          split2_bf16(y[4 * j], y[4 * j + 1], hi2[j].x, lo2[j].x);
+          split2_bf16(y[4 * j + 2], y[4 * j + 3], hi2[j].y, lo2[j].y);
+        }
+        if (ovalid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (o.f32) *reinterpret_cast<float4*>(o.f32 + orow * o.ld + c0 + 64 * j) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            if (o.pl && p.out_planes > 0) {
+              __nv_bfloat16* dh = o.pl + orow * o.ld + c0 + 64 * j;
+              *reinterpret_cast<uint2*>(dh) = hi2[j];
+              if (p.out_planes > 1) *reinterpret_cast<uint2*>(dh + static_cast<long>(o.rows_alloc) * o.ld) = lo2[j];
+            }
+          }
+        }
+        if (e == 0 && lane == 0) SSTAMP(18 + 20 * pr);
+        if (!last && own) {
+          // next X operand into every CTA of the cluster: k-block j, 8 bytes inside swizzle chunk (c0 >> 3)
+          const uint32_t rowoff = (otcl >> 3) * 1024 + (otcl & 7) * 128 + ((((c0 >> 3) ^ (otcl & 7)) << 4) | ((c0 & 7) * 2));
 #pragma unroll
           for (int k = 0; k < C::CL; ++k) {
-            const uint32_t base = tc::mapa(xop_local, k) + off;
-            st_cluster_v4u(base, hi4);
-            if (NSPLIT == 2) st_cluster_v4u(base + XT, lo4);
+            const uint32_t base = tc::mapa(xop_local, k) + rowoff;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              st_cluster_v2u(base + (j * NSPLIT) * XT, hi2[j].x, hi2[j].y);
+              if (NSPLIT == 2) st_cluster_v2u(base + (j * NSPLIT + 1) * XT, lo2[j].x, lo2[j].y);
+            }
           }
-        }
         }
       }
       if (e == 0 && lane == 0) SSTAMP(16 + 20 * pr);

@@ -79,7 +79,7 @@ struct Weight {
 struct ActBuf {
   Act act{nullptr, nullptr, 0, 0};
   CUtensorMap map;    // TMA box of 128 rows x 64 columns
-  CUtensorMap map16;  // box of 16 rows (k_ffn_swap token groups)
+  CUtensorMap map16, map32, map48;  // boxes of 16 / 32 / 48 rows (k_ffn_swap token groups)
   bool has_map = false;
 };
 
@@ -192,6 +192,8 @@ int alloc_act(H* h, Arena& ar, ActBuf* b, int rows, int ld, bool f32, bool plane
     CK(cudaMemset(b->act.pl, 0, 2 * n * sizeof(__nv_bfloat16)));
     CKS(make_map(h, &b->map, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 128));
     CKS(make_map(h, &b->map16, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 16));
+    CKS(make_map(h, &b->map32, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 32));
+    CKS(make_map(h, &b->map48, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 48));
     b->has_map = true;
   }
   return LADIFF_OK;
@@ -454,11 +456,12 @@ int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
     a.rt = rt;
     if (a.trace) h->trace_names[h->trace_n - 1] = "ffn_swap M" + std::to_string(c.M_max) + " rt" + std::to_string(rt);
     dim3 grid((c.M_max + rt - 1) / rt, 4);
+    const CUtensorMap& mx = rt == 16 ? c.X->map16 : (rt == 32 ? c.X->map32 : c.X->map48);
     if (mode == LADIFF_MODE_BF16X3)
-      CK(launch_pdl(k_ffn_swap<2>, grid, dim3(SwapCfg<2>::THREADS), SwapCfg<2>::smem_bytes(rt), st, c.X->map16, q0.W1->map128,
+      CK(launch_pdl(k_ffn_swap<2>, grid, dim3(SwapCfg<2>::THREADS), SwapCfg<2>::smem_bytes(rt), st, mx, q0.W1->map128,
                     q0.W2->map128, q1.W1->map128, q1.W2->map128, a));
     else
-      CK(launch_pdl(k_ffn_swap<1>, grid, dim3(SwapCfg<1>::THREADS), SwapCfg<1>::smem_bytes(rt), st, c.X->map16, q0.W1->map128,
+      CK(launch_pdl(k_ffn_swap<1>, grid, dim3(SwapCfg<1>::THREADS), SwapCfg<1>::smem_bytes(rt), st, mx, q0.W1->map128,
                     q0.W2->map128, q1.W1->map128, q1.W2->map128, a));
     h->launches++;
     return LADIFF_OK;
