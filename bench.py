@@ -229,14 +229,52 @@ def run_own(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- pipelined over the K steps (LADIFF.sample_stream): the K batches are independent, batch i is decoded on a
+    # low-priority stream while batch i+1 runs its reverse loop.  Same work, same results; one event pair around the K steps.
+    def batches(n, host):
+        for _ in range(n):
+            flush.fill_(1.0)                                  # L2 flush between iterations (inside the timed region here)
+            if host:
+                yield text_h.to(dev, non_blocking=True), lengths, noise_h.to(dev, non_blocking=True)
+            else:
+                yield text_d, lengths, noise_d
+
+    def run_pipe(n, host):
+        for feats in model.sample_stream(batches(n, host)):
+            if world > 1:
+                dist.all_gather(gather, feats)                # the only collective: motions over NVLink
+            if host:
+                out_h.copy_(feats, non_blocking=True)
+
+    def timed_pipe(K, W, host):
+        run_pipe(W, host)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_pipe(K, host)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     W = max(args.warmup, 3)
     _, launches = step_resident()                             # builds plans / graphs
+    pipelined = not args.no_pipeline
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = timed(lambda: step_resident(), args.steps, W)
+    ms_seq = timed(lambda: step_resident(), args.steps, W)    # one batch at a time (latency view)
+    ms_total = timed_pipe(args.steps, W, False) if pipelined else ms_seq
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, W)
+    ms_e2e = timed_pipe(args.steps, W, True) if pipelined else timed(step_e2e, args.steps, W)
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
@@ -328,7 +366,10 @@ def run_own(args):
         "data": "synthetic",
         "config": {"workload": f"LA-DDPM sampling batch {B} per GPU, {STEPS_DDIM}-step DDIM + CFG {GUIDANCE}, {FRAMES} frames, + LA-VAE decode to {NFEATS}-d features",
                    "weights": "random-init (reference initialiser families), seed 1234", "mode": args.mode,
-                   "l2": "L2 flushed (256 MiB write) between timed iterations", "collective": "all_gather of motions per step" if world > 1 else "none"},
+                   "l2": "L2 flushed (256 MiB write) between timed iterations", "collective": "all_gather of motions per step" if world > 1 else "none",
+                   "schedule": ("pipelined over the K steps (LADIFF.sample_stream: decode of batch i on a low-priority stream under the reverse "
+                                "loop of batch i+1)") if pipelined else "one batch at a time"},
+        "latency_ms_per_batch": ms_seq / args.steps, "value_sequential": world * B * args.steps / (ms_seq / 1e3),
         "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": int(text_h.numel() * 4 + noise_h.numel() * 4),
                 "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches * args.steps),
@@ -347,7 +388,7 @@ def run_own(args):
             "bound": "tensor", "achieved": ach_k, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": ach_k / peaks["bf16_burst"],
             "traffic": NCU_DRAM_BYTES.get(dom["kernel"]), "kernel": dom["kernel"], "us_per_launch": dom["us_per_launch"],
             "launches_per_step": dom["launches_per_step"],
-            "share_of_step": dom["us_per_launch"] * 1e-3 * dom["launches_per_step"] / ms_step,
+            "share_of_step": dom["us_per_launch"] * 1e-3 * dom["launches_per_step"] / (ms_seq / args.steps),
             "note": ("algorithmic FLOPs per launch = 1280 rows x 4 x lin(256,1024) (the two feed-forward pairs of one denoiser layer, "
                      "SURVEY.md 8d rows 'sa ReLU-FFN' + 'GELU FFN'); bf16x3 issues 3x these on the tensor pipe; duration = CUDA events "
                      f"around 200 back-to-back launches; peak = bf16 burst of {peaks['source']}; traffic = dram read+write per launch "
@@ -367,6 +408,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-pipeline", action="store_true", help="time one batch at a time instead of LADIFF.sample_stream")
     ap.add_argument("--quick", action="store_true", help="skip the extra measurements (kernel table, other modes, CPU baseline)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -62,6 +62,7 @@ class LADIFF(nn.Module):
         self.do_classifier_free_guidance = self.guidance_scale > 1.0
         self.feats2joints = datamodule.feats2joints
         self._shared_engine = None
+        self._pipe_streams = None
         self.times: List[float] = []
 
     # -- engine plumbing ------------------------------------------------------------------------------------
@@ -158,6 +159,49 @@ class LADIFF(nn.Module):
         """_diffusion_reverse + vae.decode without leaving the device: [B, max(lengths), nfeats] CUDA tensor."""
         z = self._diffusion_reverse(encoder_hidden_states, lengths, latents=latents, generator=generator)
         return self.vae.decode(z, lengths)
+
+    @torch.no_grad()
+    def sample_stream(self, batches):
+        """Pipelined ``sample_features`` over an iterable of ``(encoder_hidden_states, lengths, latents_or_None)``.
+
+        Prompt batches are independent, and the two halves of the path load the GPU very differently: the 50-step reverse
+        loop is a latency-bound chain of small launches (~110 of 148 SMs, mostly waiting), the LA-VAE decode is throughput
+        work.  Batch i is therefore decoded on a low-priority side stream while batch i+1 already runs its reverse loop on a
+        high-priority stream.  Yields the ``[B, max(lengths), nfeats]`` CUDA tensors in input order, bit-identical to
+        ``sample_features``; a yielded tensor is ordered after its producer on the caller's current stream."""
+        self._bind()
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_pipe_streams", None) is None or self._pipe_streams[0].device != cur.device:
+            self._pipe_streams = (torch.cuda.Stream(device=cur.device, priority=-1), torch.cuda.Stream(device=cur.device, priority=0))
+        rev, dec = self._pipe_streams
+        dec.wait_stream(cur)
+        pending = None
+        for text, lengths, lat in batches:
+            rev.wait_stream(cur)                       # inputs were produced (copied) on the caller's stream
+            with torch.cuda.stream(rev):
+                z = self._diffusion_reverse(text, lengths, latents=lat)
+                ev = torch.cuda.Event()
+                ev.record(rev)
+            for t in (text, lat):
+                if t is not None:
+                    t.record_stream(rev)
+            if pending is not None:                    # hand out batch i only after batch i+1 has been enqueued
+                feats, dev = pending
+                cur.wait_event(dev)
+                feats.record_stream(cur)
+                yield feats
+            dec.wait_event(ev)
+            with torch.cuda.stream(dec):
+                z.record_stream(dec)
+                feats = self.vae.decode(z, lengths)
+                dev = torch.cuda.Event()
+                dev.record(dec)
+            pending = (feats, dev)
+        if pending is not None:
+            feats, dev = pending
+            cur.wait_event(dev)
+            feats.record_stream(cur)
+            yield feats
 
     def t2m_eval(self, batch):
         raise NotImplementedError("t2m_eval needs the pretrained T2M evaluators and datasets (SURVEY.md 8f row 3)")

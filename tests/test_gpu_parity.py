@@ -159,3 +159,27 @@ def test_batch128_properties(engine, mode):
     tol = {"bf16x3": 2e-3, "bf16": 0.25}[mode]
     err = (fs - f1[idx]).abs().max().item()
     assert err < tol, f"a sample's result must not depend on its batch neighbours (max-abs diff {err:.3e})"
+
+
+def test_sample_stream_matches_sequential(oracle_sd):
+    """LADIFF.sample_stream (decode of batch i overlapped with the reverse loop of batch i+1 on two streams) returns exactly
+    what the one-batch-at-a-time path returns, in order, for batches of different sizes / lengths."""
+    import ladiff_b200 as L
+    from ladiff_b200.data import SyntheticDataModule
+    from ladiff_b200.modeltype import LADIFF
+    torch.set_grad_enabled(False)
+    model = LADIFF(L.default_config("humanml3d", num_inference_timesteps=6), SyntheticDataModule(263, 22))
+    model.denoiser.load_state_dict(O.sub(oracle_sd, "denoiser."), strict=True)
+    model.vae.load_state_dict(O.sub(oracle_sd, "vae."), strict=True)
+    model = model.to("cuda:0").eval()
+    g = torch.Generator().manual_seed(77)
+    batches = []
+    for B, lengths in ((3, [196, 52, 120]), (5, [40, 44, 196, 100, 148]), (3, [196, 52, 120]), (3, [64, 64, 64])):
+        batches.append((torch.randn((2 * B, 1, 768), generator=g).cuda(), lengths, torch.randn((B, 5, 256), generator=g).cuda()))
+    seq = [model.sample_features(t, l, latents=n).clone() for t, l, n in batches]
+    torch.cuda.synchronize()
+    out = [f.clone() for f in model.sample_stream(iter(batches))]
+    torch.cuda.synchronize()
+    assert len(out) == len(seq)
+    for a, b in zip(seq, out):
+        assert a.shape == b.shape and torch.equal(a, b)
