@@ -219,15 +219,19 @@ class Engine:
                                                 EPI[epilogue], mode, _ptr(out), _stream()), "linear_test")
         return out
 
-    def trace_read(self, max_launches: int = 16384):
-        """[(name, start, wait_done, accum_ready, done)] in ns of the last diffusion_reverse (needs LADIFF_TRACE=1)."""
+    def trace_read(self, max_launches: int = 16384, extra: bool = False):
+        """[(name, start, wait_done, accum_ready, done)] in ns of the last diffusion_reverse (needs LADIFF_TRACE=1);
+        extra=True appends the four kernel-specific stamps (slots 4..7; 0 where a kernel does not use them)."""
         buf = (C.c_uint64 * (8 * max_launches))()
         names = C.create_string_buffer(96 * max_launches)
         n = self.lib.ladiff_trace_read(self._h, buf, max_launches, names, 96)
         out = []
         for i in range(n):
             nm = names.raw[96 * i:96 * (i + 1)].split(b"\0", 1)[0].decode()
-            out.append((nm, int(buf[8 * i]), int(buf[8 * i + 1]), int(buf[8 * i + 2]), int(buf[8 * i + 3])))
+            rec = (nm, int(buf[8 * i]), int(buf[8 * i + 1]), int(buf[8 * i + 2]), int(buf[8 * i + 3]))
+            if extra:
+                rec = rec + tuple(int(buf[8 * i + k]) for k in range(4, 8))
+            out.append(rec)
         return out
 
     def ffn_test(self, x: torch.Tensor, layer: int, mod: torch.Tensor, mode: int = MODE_BF16X3, fused=True, iters: int = 0):

@@ -41,6 +41,21 @@ struct FfnArgs {
   int out_planes;
   int x_plane_rows;      // row offset of the lo plane in the X tensor map
   int rt;                // k_ffn_swap: tokens per cluster (16 / 32 / 48)
+  // k_ffn_swap with the sa_block attention fused in front (rt == 48 only): instead of loading X by TMA, every CTA computes
+  //   x1[row] = LN( Xin[row] + b_o + sum_h sum_j softmax_j(q_h . k_hj / 8) v'_hj )   (see k_attn_ln in kernels.cuh)
+  // for its 12 owned rows from the extended in-projection buffer and broadcasts it as the X operand of the cluster
+  int att;                         // 1: fused attention prologue
+  const float* att_qkvx;           // [rows, 1792]: q | k | 4 x v' | X
+  const int* att_off;              // [S + 1] row offsets of the sequences
+  const int* att_row_seq;          // [rows] sequence of a row
+  const float* att_textkv;         // per-sequence conditioning row: k | 4 x v'
+  int att_ld_textkv;
+  const float* att_timekv;         // this (step, layer)'s time-token row: k | 4 x v'
+  const float* att_res;            // layer input rows (residual), ld att_ld_res
+  int att_ld_res;
+  const float *att_bo, *att_g, *att_b;   // out_proj bias, norm1 weight / bias
+  Act att_x1;                      // fp32 master of x1 (residual of pair 0)
+  Act att_xcopy;                   // optional copy of the layer input (U-Net skip source), fp32 and/or planes
   int w1_plane_rows[2], w2_plane_rows[2];
   unsigned long long* trace;
   long long* dbg;        // optional per-CTA clock64 stamps [ncta][48] (ladiff_ffn_test with LADIFF_DBG_STAMPS=1)

@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "ffn_cluster.cuh"
+#include "kernels.cuh"
 #include "linear.cuh"
 #include "tc_ptx.cuh"
 
@@ -62,6 +63,188 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void st_cluster_v4u(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// sa_block attention + out-proj (folded into the values) + residual + LayerNorm for the 12 rows this CTA owns, executed by the
+// 256 epilogue threads (mdiff_transformer.py:54-62,296-313; same arithmetic as k_attn_ln, kernels.cuh).  Thread (cp, hs):
+// output columns 2 cp, 2 cp + 1 of the owned rows 6 hs .. 6 hs + 5.  `scratch` is the (still unused) h / receive region:
+//   Ks[20][256] latent key rows of every touched sequence | Ts[12][256] text-token keys | Tm[256] time-token key |
+//   Qs[12][256] (pre-scaled by 1/8) | Ps[12][4][8] | red[2][8][6]
+// x1 goes (i) as fp32 to p.att_x1 (the residual the owners of pair 0 read back), (ii) as bf16 hi/lo planes into the X operand of
+// all four CTAs of the cluster (token-major, K-major, 128-byte swizzle).
+template <int NSPLIT>
+__device__ __forceinline__ void swap_attention_prologue(const FfnArgs& p, uint8_t* scratch, uint32_t xop_local, int XT, int row0,
+                                                        int rank, int tpc, int M, int et) {
+  constexpr int MAXT = 5, NK = MAXT + 2, OWN = 12, HALF = 6;
+  float* Ks = reinterpret_cast<float*>(scratch);   // [20][256]
+  float* Ts = Ks + 20 * 256;                       // [12][256]
+  float* Tm = Ts + 12 * 256;                       // [256]
+  float* Qs = Tm + 256;                            // [12][256]
+  float* Ps = Qs + 12 * 256;                       // [12][4][8]
+  float* red = Ps + 12 * 4 * 8;                    // [2][8][6]
+  const int R0 = row0 + rank * tpc;                // first owned row
+  const int nown = max(0, min(OWN, M - R0));       // valid owned rows (tpc == 12)
+  const int lane = et & 31, wrp = et >> 5;
+  const int cp = et & 127, hs = et >> 7, c = 2 * cp;
+  if (nown > 0) {
+    const int s0 = __ldg(p.att_row_seq + R0), s1 = __ldg(p.att_row_seq + R0 + nown - 1);
+    const int Rk0 = __ldg(p.att_off + s0), Rk1 = __ldg(p.att_off + s1 + 1);   // latent key rows [Rk0, Rk1): at most 20
+    // ---- stage keys / queries: thread = column
+    for (int j = 0; j < Rk1 - Rk0; ++j) Ks[j * 256 + et] = p.att_qkvx[static_cast<long>(Rk0 + j) * DQX_LD + 256 + et];
+    for (int s = s0; s <= s1; ++s) Ts[(s - s0) * 256 + et] = p.att_textkv[static_cast<long>(s) * p.att_ld_textkv + et];
+    Tm[et] = p.att_timekv[et];
+    for (int i = 0; i < nown; ++i) Qs[i * 256 + et] = 0.125f * p.att_qkvx[static_cast<long>(R0 + i) * DQX_LD + et];
+  }
+  // per owned row of this thread's half: sequence, first row of the sequence, number of latent keys
+  int rs_[HALF], rr0[HALF], rm[HALF];
+  float2 xr[HALF];
+#pragma unroll
+  for (int u = 0; u < HALF; ++u) {
+    const int i = hs * HALF + u;
+    rs_[u] = -1; rr0[u] = 0; rm[u] = 0;
+    xr[u] = make_float2(0.f, 0.f);
+    if (i < nown) {
+      const int s = __ldg(p.att_row_seq + R0 + i);
+      rs_[u] = s;
+      rr0[u] = __ldg(p.att_off + s);
+      rm[u] = min(__ldg(p.att_off + s + 1) - rr0[u], MAXT);
+      xr[u] = *reinterpret_cast<const float2*>(p.att_res + static_cast<long>(R0 + i) * p.att_ld_res + c);
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (et == 0) trace_mark(p.trace, 4);
+  if (nown > 0) {
+    const int s0 = __ldg(p.att_row_seq + R0);
+    const int Rk0 = __ldg(p.att_off + s0);
+    // ---- scores: element e = (i, h, j), one 64-long dot product each (d rotated by the lane: no bank conflicts)
+    for (int e = et; e < nown * 4 * 8; e += 256) {
+      const int j = e & 7, h = (e >> 3) & 3, i = e >> 5;
+      const int s = __ldg(p.att_row_seq + R0 + i);
+      const int r0 = __ldg(p.att_off + s), m = min(__ldg(p.att_off + s + 1) - r0, MAXT);
+      float sc = -INFINITY;
+      if (j < NK && (j < m || j >= MAXT)) {
+        const float* kp = (j < MAXT ? Ks + (r0 - Rk0 + j) * 256 : (j == MAXT ? Ts + (s - s0) * 256 : Tm)) + h * 64;
+        const float* qp = Qs + i * 256 + h * 64;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; d += 4) {
+          const int d0 = (d + lane) & 63, d1 = (d + 1 + lane) & 63, d2 = (d + 2 + lane) & 63, d3 = (d + 3 + lane) & 63;
+          a0 = fmaf(qp[d0], kp[d0], a0);
+          a1 = fmaf(qp[d1], kp[d1], a1);
+          a2 = fmaf(qp[d2], kp[d2], a2);
+          a3 = fmaf(qp[d3], kp[d3], a3);
+        }
+        sc = (a0 + a1) + (a2 + a3);
+      }
+      Ps[e] = sc;
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (et < nown * 4) {   // softmax over the 7 keys of (row, head)
+    float* pr_ = Ps + et * 8;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) mx = fmaxf(mx, pr_[j]);
+    float pj[NK], den = 0.f;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      pj[j] = expf(pr_[j] - mx);
+      den += pj[j];
+    }
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) pr_[j] = pj[j] * inv;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (et == 0) trace_mark(p.trace, 5);
+  // ---- out[i, c..c+1] = Xin + b_o + sum_h sum_j P[i][h][j] v'[h][j][c..c+1]; v' of a sequence is loaded once per run of rows
+  float2 acc[HALF];
+  {
+    const float2 bo = *reinterpret_cast<const float2*>(p.att_bo + c);
+    float2 v[4][NK];
+    int cur = -2;
+#pragma unroll
+    for (int u = 0; u < HALF; ++u) {
+      acc[u] = make_float2(bo.x + xr[u].x, bo.y + xr[u].y);
+      if (rs_[u] >= 0) {
+        if (rs_[u] != cur) {
+          cur = rs_[u];
+          const float* tk = p.att_textkv + static_cast<long>(cur) * p.att_ld_textkv;
+#pragma unroll
+          for (int j = 0; j < NK; ++j) {
+            const bool on = j < rm[u] || j >= MAXT;
+            const float* base = j < MAXT ? p.att_qkvx + static_cast<long>(rr0[u] + j) * DQX_LD + 512 : (j == MAXT ? tk + 256 : p.att_timekv + 256);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) v[h][j] = on ? *reinterpret_cast<const float2*>(base + h * 256 + c) : make_float2(0.f, 0.f);
+          }
+        }
+        const float* pp = Ps + (hs * HALF + u) * 32;
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int j = 0; j < NK; ++j) {
+            const float w = pp[h * 8 + j];   // masked keys: P == 0 (score -inf) and v == 0
+            acc[u].x = fmaf(w, v[h][j].x, acc[u].x);
+            acc[u].y = fmaf(w, v[h][j].y, acc[u].y);
+          }
+      }
+    }
+  }
+  if (et == 0) trace_mark(p.trace, 6);
+  // ---- LayerNorm over the 256 columns of each row: 128 threads (4 warps) of this half hold them
+  float mean[HALF];
+#pragma unroll
+  for (int u = 0; u < HALF; ++u) {
+    const float w = warp_sum(acc[u].x + acc[u].y);
+    if (lane == 0) red[(0 * 8 + wrp) * HALF + u] = w;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+  for (int u = 0; u < HALF; ++u) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) t += red[(0 * 8 + hs * 4 + w) * HALF + u];
+    mean[u] = t * (1.f / 256.f);
+    const float dx = acc[u].x - mean[u], dy = acc[u].y - mean[u];
+    const float w = warp_sum(dx * dx + dy * dy);
+    if (lane == 0) red[(1 * 8 + wrp) * HALF + u] = w;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const float2 gc = *reinterpret_cast<const float2*>(p.att_g + c), bc = *reinterpret_cast<const float2*>(p.att_b + c);
+#pragma unroll
+  for (int u = 0; u < HALF; ++u) {
+    const int i = hs * HALF + u;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) t += red[(1 * 8 + hs * 4 + w) * HALF + u];
+    const float rstd = 1.0f / sqrtf(t * (1.f / 256.f) + LD_EPS);
+    const bool valid = i < nown;
+    const float y0 = valid ? (acc[u].x - mean[u]) * rstd * gc.x + bc.x : 0.f;
+    const float y1 = valid ? (acc[u].y - mean[u]) * rstd * gc.y + bc.y : 0.f;
+    uint32_t hi, lo;
+    split2_bf16(y0, y1, hi, lo);
+    if (valid) {
+      const long row = R0 + i;
+      *reinterpret_cast<float2*>(p.att_x1.f32 + row * p.att_x1.ld + c) = make_float2(y0, y1);
+      if (p.att_xcopy.f32) *reinterpret_cast<float2*>(p.att_xcopy.f32 + row * p.att_xcopy.ld + c) = xr[u];
+      if (p.att_xcopy.pl && p.out_planes > 0) {
+        uint32_t xh, xl;
+        split2_bf16(xr[u].x, xr[u].y, xh, xl);
+        __nv_bfloat16* dh = p.att_xcopy.pl + row * p.att_xcopy.ld + c;
+        *reinterpret_cast<uint32_t*>(dh) = xh;
+        if (p.out_planes > 1) *reinterpret_cast<uint32_t*>(dh + static_cast<long>(p.att_xcopy.rows_alloc) * p.att_xcopy.ld) = xl;
+      }
+    }
+    // X operand of every CTA of the cluster: token tcl, k-block c / 64, 4 bytes inside swizzle chunk (c & 63) / 8
+    const int tcl = rank * tpc + i;
+    const uint32_t off = (c >> 6) * NSPLIT * XT + (tcl >> 3) * 1024 + (tcl & 7) * 128 + (((((c & 63) >> 3) ^ (tcl & 7)) << 4) | ((c & 7) * 2));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t base = tc::mapa(xop_local, k) + off;
+      asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(base), "r"(hi) : "memory");
+      if (NSPLIT == 2) asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(base + XT), "r"(lo) : "memory");
+    }
+  }
 }
 
 template <int NSPLIT>
@@ -168,7 +351,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       trace_mark(p.trace, 1);
       SSTAMP(1);
     }
-    if (tc::elect_one()) {
+    if (!p.att && tc::elect_one()) {
       for (int kb = 0; kb < 4; ++kb) {
         tc::mbar_expect_tx(&x_full[kb], NSPLIT * XT);
         for (int pl = 0; pl < NSPLIT; ++pl)   // tmX has a box of rt rows
@@ -176,6 +359,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       }
     }
     __syncwarp();
+    if (p.att) tc::cluster_sync();  // #0: x1 has been broadcast by the attention prologue of every CTA
     for (int pr = 0; pr < p.npairs; ++pr) {
       // every load whose slot is freed by MMAs of pairs <= pr can be issued before this pair's cluster barriers
       const int lim = min(total, 16 * (pr + 1) + nst);
@@ -194,13 +378,17 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
     const uint32_t idesc = tc::idesc_bf16_f32(128, rt);
     const uint32_t ring_u = tc::smem_u32(ring), xop_u = tc::smem_u32(xop), hr_u = tc::smem_u32(hr);
+    if (p.att) {
+      tc::cluster_sync();  // #0
+      fence_proxy_async_all();
+    }
     for (int pr = 0; pr < p.npairs; ++pr) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const int slot = r & 3, ph = r >> 3;   // 16 stages per pair: slot = (16 pr + r) & 3; stage order: see issue_load
         const int g = ph ? (r >> 1) & 1 : (r >> 2) & 1, kb = ph ? ((r >> 2) & 1) * 2 + (r & 1) : r & 3;
         if (ph == 0) {
-          if (pr == 0) tc::mbar_wait(&x_full[kb], 0);
+          if (pr == 0 && !p.att) tc::mbar_wait(&x_full[kb], 0);
         } else if ((r & 3) == 0) {
           tc::mbar_wait(&hfull[kb >> 1], pr & 1);
         }
@@ -260,6 +448,12 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     const long orow = static_cast<long>(row0) + otcl;
     const bool ovalid = own && orow < M;
     tc::pdl_wait();
+    if (p.att) {
+      swap_attention_prologue<NSPLIT>(p, hr, xop_local, XT, row0, static_cast<int>(rank), tpc, M, threadIdx.x - 64);
+      if (threadIdx.x == 64) trace_mark(p.trace, 7);
+      fence_proxy_async_all();
+      tc::cluster_sync();  // #0: every CTA's x1 rows have landed in every X operand; x1 fp32 (global) is visible to the owners
+    }
     // owner-side operands straight into registers while the mainloop runs: va = residual (pair 0) / 1 + scale (pair 1),
     // vb = hoisted ca_block delta (pair 0) / shift (pair 1)
     float va[16], vb[16];
@@ -269,7 +463,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       if (p.res) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 a = *reinterpret_cast<const float4*>(p.res + orow * C::D + c0 + 64 * j);
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(p.res + orow * C::D + c0 + 64 * j));
           va[4 * j] = a.x; va[4 * j + 1] = a.y; va[4 * j + 2] = a.z; va[4 * j + 3] = a.w;
         }
       }

@@ -390,6 +390,13 @@ struct FfnCall {
   int out_planes = 0;
   long long* dbg = nullptr;
   bool force_cluster = false;  // tests: the 128-row cluster kernel even where the swapped kernel would be chosen
+  // fused sa_block attention prologue (k_ffn_swap, rt == 48): X is computed in the kernel instead of being loaded
+  bool att = false;
+  const float *att_qkvx = nullptr, *att_textkv = nullptr, *att_timekv = nullptr, *att_res = nullptr;
+  const float *att_bo = nullptr, *att_g = nullptr, *att_b = nullptr;
+  const int *att_off = nullptr, *att_row_seq = nullptr;
+  int att_ld_textkv = 0, att_ld_res = 0;
+  Act att_x1{nullptr, nullptr, 0, 0}, att_xcopy{nullptr, nullptr, 0, 0};
 };
 
 bool ffn_cluster_enabled() { return getenv("LADIFF_NO_FFN_CLUSTER") == nullptr; }
@@ -405,6 +412,13 @@ int ffn_swap_rt(int M_max) {
   for (int rt = 16; rt <= 48; rt += 16)
     if (((M_max + rt - 1) / rt) * 4 <= 148) return rt;
   return 0;
+}
+// the attention prologue of k_ffn_swap stages the keys of its 12 owned rows in the 48 KB h region: token groups of 48 only
+// Opt-in (LADIFF_ATT_FUSE=1): measured SLOWER on B200 than the separate k_attn_ln launch (reverse loop 23.9 vs 22.0 ms at B = 128,
+// profiles/r01g_trace_att_fused.txt): 12 rows per CTA on 256 threads serialise three dependent global round trips (~1.8 us each).
+bool ffn_att_fusable(int M_max, int T) {
+  const char* e = getenv("LADIFF_ATT_FUSE");
+  return e && atoi(e) == 1 && T <= 5 && ffn_swap_rt(M_max) == 48;
 }
 
 int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
@@ -452,9 +466,16 @@ int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
   const FfnPair& q0 = c.pair[0];
   const FfnPair& q1 = c.pair[c.npairs - 1];
   const int rt = c.force_cluster ? 0 : ffn_swap_rt(c.M_max);
+  if (c.att && rt != 48) return h->err.set(LADIFF_ERR_INVALID, "ffn swap: the fused attention prologue needs token groups of 48");
   if (rt > 0) {
     a.rt = rt;
-    if (a.trace) h->trace_names[h->trace_n - 1] = "ffn_swap M" + std::to_string(c.M_max) + " rt" + std::to_string(rt);
+    if (c.att) {
+      a.att = 1;
+      a.att_qkvx = c.att_qkvx; a.att_off = c.att_off; a.att_row_seq = c.att_row_seq; a.att_textkv = c.att_textkv;
+      a.att_ld_textkv = c.att_ld_textkv; a.att_timekv = c.att_timekv; a.att_res = c.att_res; a.att_ld_res = c.att_ld_res;
+      a.att_bo = c.att_bo; a.att_g = c.att_g; a.att_b = c.att_b; a.att_x1 = c.att_x1; a.att_xcopy = c.att_xcopy;
+    }
+    if (a.trace) h->trace_names[h->trace_n - 1] = std::string(c.att ? "attn+ffn_swap M" : "ffn_swap M") + std::to_string(c.M_max) + " rt" + std::to_string(rt);
     dim3 grid((c.M_max + rt - 1) / rt, 4);
     const CUtensorMap& mx = rt == 16 ? c.X->map16 : (rt == 32 ? c.X->map32 : c.X->map48);
     if (mode == LADIFF_MODE_BF16X3)
@@ -909,12 +930,15 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   const int mode = p->mode, pl = p->planes, R = p->Rmax, S = p->S, n = p->n;
   LinCall c;
   unsigned long long* tr = nullptr;
-  if (h->trace && h->trace_n < h->trace_cap) {
+  const bool fuse_att = mode != LADIFF_MODE_FP32 && ffn_cluster_enabled() && ffn_att_fusable(R, p->T);
+  if (!fuse_att && h->trace && h->trace_n < h->trace_cap) {
     tr = h->trace + 8ull * h->trace_n;
     if (static_cast<int>(h->trace_names.size()) <= h->trace_n) h->trace_names.resize(h->trace_n + 1);
     h->trace_names[h->trace_n++] = "attn_ln M" + std::to_string(R) + " ";
   }
-  if (p->T <= 5)
+  if (fuse_att) {
+    // attention + out-proj + residual + LN run as the prologue of the FFN kernel (one launch per layer after the in-projection)
+  } else if (p->T <= 5)
     LAUNCHP(k_attn_ln<5>, S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
   else
@@ -931,6 +955,15 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
     f.pair[1].W1 = &w.gff1; f.pair[1].W2 = &w.gff2; f.pair[1].act = EPI_GELU; f.pair[1].kind = EPI_LN_MOD_SILU;
     f.pair[1].ln_g = w.ffn_sn_g; f.pair[1].ln_b = w.ffn_sn_b;
     f.pair[1].mod = p->mod + static_cast<size_t>(step) * NL * 1024 + l * 1024 + 512; f.pair[1].out = p->sbuf.act;
+    if (fuse_att) {
+      f.att = true;
+      f.att_qkvx = p->qkv; f.att_off = p->off; f.att_row_seq = p->row_seq;
+      f.att_textkv = p->textkv + l * DC_LD; f.att_ld_textkv = NL * DC_LD;
+      f.att_timekv = p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD;
+      f.att_res = res; f.att_ld_res = ld_res;
+      f.att_bo = w.out_bias; f.att_g = w.n1g; f.att_b = w.n1b;
+      f.att_x1 = p->x1.act; f.att_xcopy = xcopy;
+    }
     return launch_ffn_cluster(h, st, mode, f);
   }
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
@@ -1319,7 +1352,7 @@ int ladiff_trace_read(ladiff_handle* h, uint64_t* out_host, int32_t max_launches
   if (n > max_launches) n = max_launches;
   cudaMemcpy(out_host, h->trace, 8ull * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   for (int i = 0; i < n; ++i) {
-    for (int s = 1; s < 4; ++s) out_host[8 * i + s] = ~out_host[8 * i + s];
+    for (int s = 1; s < 8; ++s) out_host[8 * i + s] = ~out_host[8 * i + s];
     if (names_host && name_stride > 0) snprintf(names_host + static_cast<size_t>(i) * name_stride, name_stride, "%s", h->trace_names[i].c_str());
   }
   cudaMemset(h->trace, 0xFF, 8ull * h->trace_cap * sizeof(unsigned long long));

@@ -27,7 +27,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 eng.trace_read()          # clear
 model._diffusion_reverse(text, lengths, latents=noise)
-tr = [t for t in eng.trace_read() if t[1] < (1 << 63)]
+tr = [t for t in eng.trace_read(extra=True) if t[1] < (1 << 63)]
 tr.sort(key=lambda t: t[1])
 # steady-state: launches of the middle step
 per_step = [t for t in tr if "M%d " % (2 * B * 5) in t[0]]
@@ -37,9 +37,11 @@ print(f"{len(tr)} traced launches, {n} per step; step {n_steps // 2}:")
 print(f"{'kernel':28s} {'start':>8s} {'dep-wait':>9s} {'accum':>8s} {'done':>8s} | {'dur':>6s} {'gap-to-next-start':>8s} {'prev-done->wait':>8s}")
 t0 = mid[0][1]
 prev_done = None
-for i, (nm, s, w, a, d) in enumerate(mid):
+for i, (nm, s, w, a, d, *xs) in enumerate(mid):
     nxt = mid[i + 1][1] if i + 1 < len(mid) else None
     print(f"{nm:28s} {(s - t0) / 1e3:8.2f} {(w - t0) / 1e3:9.2f} {(a - t0) / 1e3:8.2f} {(d - t0) / 1e3:8.2f} | {(d - s) / 1e3:6.2f} "
           f"{((nxt - d) / 1e3 if nxt else 0):8.2f} {((w - prev_done) / 1e3 if prev_done else 0):8.2f}")
+    if any(0 < x < (1 << 63) for x in xs):
+        print("    kernel stamps 4..7 (us after dep-wait): " + " ".join(f"{(x - w) / 1e3:7.2f}" if 0 < x < (1 << 63) else "      -" for x in xs))
     prev_done = d
 print(f"step span {(mid[-1][4] - mid[0][1]) / 1e3:.1f} us")

@@ -161,6 +161,31 @@ def test_batch128_properties(engine, mode):
     assert err < tol, f"a sample's result must not depend on its batch neighbours (max-abs diff {err:.3e})"
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_denoiser_forward_large_batch_vs_oracle(engine, oracle_sd, mode, ragged, monkeypatch):
+    """One denoiser.forward at the batch of the headline config (token groups of 48, the sa_block attention fused into the
+    feed-forward kernel), full-length and ragged (sequences of 1..5 latent rows, so the 12 rows a CTA owns span several
+    sequences and the last groups are partly / wholly empty), against the CPU oracle and against the unfused kernels."""
+    from ladiff_b200._lib import MODES
+    monkeypatch.setenv("LADIFF_ATT_FUSE", "1")     # opt-in path (measured slower than the separate launch, DESIGN.md section 8)
+    B = 128      # 2 * 128 * 5 = 1280 row slots -> token groups of 48 whatever the lengths are (the plan is sized for the maximum)
+    text, noise, lengths = O.synthetic_inputs(B, seed=4321, ragged=ragged)
+    x = O.initial_latents(noise, lengths)
+    mie = O.max_iter_elements_of(lengths).tolist() * 2
+    out = engine.denoiser_forward(torch.cat([x] * 2).cuda(), 481, text.cuda(), mie, MODES[mode]).cpu()
+    ref = O.denoiser_forward(oracle_sd, torch.cat([x] * 2), torch.tensor(481), text, torch.tensor(mie))
+    valid = O.latent_mask_of(torch.tensor(mie))
+    err = (out - ref)[valid].abs().max().item()
+    tol = {"bf16x3": 2e-4, "bf16": 0.1}[mode]
+    assert (out[~valid] == 0).all()
+    assert err < tol, f"{mode} ragged={ragged}: fused path max-abs err {err:.3e}"
+    monkeypatch.delenv("LADIFF_ATT_FUSE")
+    out2 = engine.denoiser_forward(torch.cat([x] * 2).cuda(), 481, text.cuda(), mie, MODES[mode]).cpu()
+    err2 = (out2 - out)[valid].abs().max().item()
+    assert err2 < (1e-4 if mode == "bf16x3" else 0.1), f"{mode}: fused vs unfused attention differ by {err2:.3e}"
+
+
 def test_sample_stream_matches_sequential(oracle_sd):
     """LADIFF.sample_stream (decode of batch i overlapped with the reverse loop of batch i+1 on two streams) returns exactly
     what the one-batch-at-a-time path returns, in order, for batches of different sizes / lengths."""
