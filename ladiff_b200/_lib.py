@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libladiff_b200.so")
+LIB_PATH = os.environ.get("LADIFF_LIB") or os.path.join(_HERE, "_C", "libladiff_b200.so")   # LADIFF_LIB: A/B another build
 
 MODE_FP32, MODE_BF16X3, MODE_BF16 = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}

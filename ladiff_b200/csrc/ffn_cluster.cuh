@@ -121,7 +121,7 @@ k_ffn_cluster(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint64_t* accb_full = bars + 14;    // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   constexpr int PV = C::HS + 5 * C::D;  // floats per pair in `vec`
 
   auto load_w1 = [&](int pr, int kb) {
@@ -152,18 +152,29 @@ k_ffn_cluster(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     tc::mbar_init(accb_full, 1);
     tc::fence_barrier_init();
     tc::fence_proxy_async();
+  }
+  if (warp == 0) {
+    __syncwarp();
     // weights never depend on the previous grid: the first two W1 k-blocks are requested before the dependency wait
-    load_w1(0, 0);
-    load_w1(0, 1);
-    tc::pdl_wait();
-    trace_mark(p.trace, 1);
-    FSTAMP(1);
-    for (int kb = 0; kb < 4; ++kb) {
-      tc::mbar_expect_tx(&x_full[kb], NSPLIT * U);
-#pragma unroll
-      for (int pl = 0; pl < NSPLIT; ++pl)
-        tc::tma_load_2d(xr + (kb * NSPLIT + pl) * U, &tmX, &x_full[kb], kb * C::BK, pl * p.x_plane_rows + tile_m * C::BM);
+    if (tc::elect_one()) {
+      load_w1(0, 0);
+      load_w1(0, 1);
     }
+    __syncwarp();
+    tc::pdl_wait();
+    if (lane == 0) {
+      trace_mark(p.trace, 1);
+      FSTAMP(1);
+    }
+    if (tc::elect_one()) {
+      for (int kb = 0; kb < 4; ++kb) {
+        tc::mbar_expect_tx(&x_full[kb], NSPLIT * U);
+#pragma unroll
+        for (int pl = 0; pl < NSPLIT; ++pl)
+          tc::tma_load_2d(xr + (kb * NSPLIT + pl) * U, &tmX, &x_full[kb], kb * C::BK, pl * p.x_plane_rows + tile_m * C::BM);
+      }
+    }
+    __syncwarp();
   }
   if (warp == 1) {
     tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -180,22 +191,27 @@ k_ffn_cluster(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 0) {
     // ===== TMA producer =====
     for (int pr = 0; pr < p.npairs; ++pr) {
-      if (lane == 0) {
+      {
         const uint32_t par = pr & 1;
         for (int kb = 0; kb < 4; ++kb) {
           tc::mbar_wait(&kb_done[kb], par);
-          if (kb < 2) load_w1(pr, kb + 2);
-          // W2 blocks whose destination (X k-blocks) is dead once k-block kb has been consumed
+          if (tc::elect_one()) {
+            if (kb < 2) load_w1(pr, kb + 2);
+            // W2 blocks whose destination (X k-blocks) is dead once k-block kb has been consumed
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int pl = 0; pl < NSPLIT; ++pl)
-              if (((j * NSPLIT + pl) * 2 + 1) / NSPLIT == kb) load_w2(pr, j, pl);
+              for (int pl = 0; pl < NSPLIT; ++pl)
+                if (((j * NSPLIT + pl) * 2 + 1) / NSPLIT == kb) load_w2(pr, j, pl);
+          }
+          __syncwarp();
         }
         if (pr + 1 < p.npairs) {
           tc::mbar_wait(accb_full, par);  // ring (W1 k-blocks 2,3 / h) is dead: prefetch the next pair's first W1 k-blocks
-          load_w1(pr + 1, 0);
-          load_w1(pr + 1, 1);
+          if (tc::elect_one()) {
+            load_w1(pr + 1, 0);
+            load_w1(pr + 1, 1);
+          }
         }
       }
       __syncwarp();
@@ -210,18 +226,22 @@ k_ffn_cluster(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // ===== MMA issuer =====
     constexpr uint32_t idesc_a = tc::idesc_bf16_f32(C::BM, C::HS);
     constexpr uint32_t idesc_b = tc::idesc_bf16_f32(C::BM, C::D);
+    const uint32_t xr_u = tc::smem_u32(xr), rr_u = tc::smem_u32(rr);
     for (int pr = 0; pr < p.npairs; ++pr) {
-      if (lane == 0) {
+      {
         const uint32_t par = pr & 1;
         // phase A: accA[128 x 128] = X . W1[slice]^T
         for (int kb = 0; kb < 4; ++kb) {
           if (pr == 0) tc::mbar_wait(&x_full[kb], 0);
           tc::mbar_wait(&w1_full[kb & 1], (kb >> 1) & 1);
           tc::tc_fence_after();
-          if (kb == 0) FSTAMP(2 + 20 * pr);
-          if (kb == 3) FSTAMP(3 + 20 * pr);
-          const uint32_t sa = tc::smem_u32(xr + kb * NSPLIT * U);
-          const uint32_t sw = tc::smem_u32(rr + (kb & 1) * C::R_STAGE);
+          if (lane == 0) {
+            if (kb == 0) FSTAMP(2 + 20 * pr);
+            if (kb == 3) FSTAMP(3 + 20 * pr);
+          }
+          const uint32_t sa = xr_u + kb * NSPLIT * U;
+          const uint32_t sw = rr_u + (kb & 1) * C::R_STAGE;
+          if (tc::elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t koff = kk * 32;
@@ -237,16 +257,19 @@ k_ffn_cluster(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             }
           }
           tc::mma_commit(&kb_done[kb]);
+          }
+          __syncwarp();
         }
         // phase B: accB[128 x 256] = h[:, slice] . W2[:, slice]^T
         for (int j = 0; j < 2; ++j) {
           tc::mbar_wait(&w2_full[j], par);
-          if (j == 0) FSTAMP(4 + 20 * pr);
+          if (j == 0 && lane == 0) FSTAMP(4 + 20 * pr);
           tc::mbar_wait(&h_full[j], par);
           tc::tc_fence_after();
-          FSTAMP(5 + j + 20 * pr);
-          const uint32_t sa = tc::smem_u32(rr + j * NSPLIT * U);
-          const uint32_t sw = tc::smem_u32(xr + j * NSPLIT * 2 * U);
+          if (lane == 0) FSTAMP(5 + j + 20 * pr);
+          const uint32_t sa = rr_u + j * NSPLIT * U;
+          const uint32_t sw = xr_u + j * NSPLIT * 2 * U;
+          if (tc::elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t koff = kk * 32;
@@ -261,8 +284,10 @@ k_ffn_cluster(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               tc::mma_bf16_ss(tmem_b, a_hi, w_hi, idesc_b, 1u);
             }
           }
+          if (j == 1) tc::mma_commit(accb_full);
+          }
+          __syncwarp();
         }
-        tc::mma_commit(accb_full);
       }
       __syncwarp();
       tc::cluster_sync();  // #1

@@ -247,7 +247,9 @@ __device__ __forceinline__ void swap_attention_prologue(const FfnArgs& p, uint8_
   }
 }
 
-template <int NSPLIT>
+// ATT: the opt-in attention prologue is a template parameter so that the default instantiation carries none of its code
+// (as a run-time branch it cost the FFN kernel 1.8 us per launch through register allocation alone).
+template <int NSPLIT, bool ATT>
 __global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(SwapCfg<NSPLIT>::THREADS, 1)
 k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1a,
            const __grid_constant__ CUtensorMap tmW2a, const __grid_constant__ CUtensorMap tmW1b,
@@ -351,7 +353,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       trace_mark(p.trace, 1);
       SSTAMP(1);
     }
-    if (!p.att && tc::elect_one()) {
+    if (!ATT && tc::elect_one()) {
       for (int kb = 0; kb < 4; ++kb) {
         tc::mbar_expect_tx(&x_full[kb], NSPLIT * XT);
         for (int pl = 0; pl < NSPLIT; ++pl)   // tmX has a box of rt rows
@@ -359,7 +361,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       }
     }
     __syncwarp();
-    if (p.att) tc::cluster_sync();  // #0: x1 has been broadcast by the attention prologue of every CTA
+    if (ATT) tc::cluster_sync();  // #0: x1 has been broadcast by the attention prologue of every CTA
     for (int pr = 0; pr < p.npairs; ++pr) {
       // every load whose slot is freed by MMAs of pairs <= pr can be issued before this pair's cluster barriers
       const int lim = min(total, 16 * (pr + 1) + nst);
@@ -378,7 +380,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
     const uint32_t idesc = tc::idesc_bf16_f32(128, rt);
     const uint32_t ring_u = tc::smem_u32(ring), xop_u = tc::smem_u32(xop), hr_u = tc::smem_u32(hr);
-    if (p.att) {
+    if (ATT) {
       tc::cluster_sync();  // #0
       fence_proxy_async_all();
     }
@@ -388,7 +390,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const int slot = r & 3, ph = r >> 3;   // 16 stages per pair: slot = (16 pr + r) & 3; stage order: see issue_load
         const int g = ph ? (r >> 1) & 1 : (r >> 2) & 1, kb = ph ? ((r >> 2) & 1) * 2 + (r & 1) : r & 3;
         if (ph == 0) {
-          if (pr == 0 && !p.att) tc::mbar_wait(&x_full[kb], 0);
+          if (pr == 0 && !ATT) tc::mbar_wait(&x_full[kb], 0);
         } else if ((r & 3) == 0) {
           tc::mbar_wait(&hfull[kb >> 1], pr & 1);
         }
@@ -448,7 +450,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     const long orow = static_cast<long>(row0) + otcl;
     const bool ovalid = own && orow < M;
     tc::pdl_wait();
-    if (p.att) {
+    if (ATT) {
       swap_attention_prologue<NSPLIT>(p, hr, xop_local, XT, row0, static_cast<int>(rank), tpc, M, threadIdx.x - 64);
       if (threadIdx.x == 64) trace_mark(p.trace, 7);
       fence_proxy_async_all();
@@ -463,7 +465,8 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       if (p.res) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 a = __ldcg(reinterpret_cast<const float4*>(p.res + orow * C::D + c0 + 64 * j));
+          const float4* rp = reinterpret_cast<const float4*>(p.res + orow * C::D + c0 + 64 * j);
+          const float4 a = ATT ? __ldcg(rp) : *rp;   // ATT: written by this CTA a moment ago -> read through L2
           va[4 * j] = a.x; va[4 * j + 1] = a.y; va[4 * j + 2] = a.z; va[4 * j + 3] = a.w;
         }
       }

@@ -478,12 +478,11 @@ int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
     if (a.trace) h->trace_names[h->trace_n - 1] = std::string(c.att ? "attn+ffn_swap M" : "ffn_swap M") + std::to_string(c.M_max) + " rt" + std::to_string(rt);
     dim3 grid((c.M_max + rt - 1) / rt, 4);
     const CUtensorMap& mx = rt == 16 ? c.X->map16 : (rt == 32 ? c.X->map32 : c.X->map48);
-    if (mode == LADIFF_MODE_BF16X3)
-      CK(launch_pdl(k_ffn_swap<2>, grid, dim3(SwapCfg<2>::THREADS), SwapCfg<2>::smem_bytes(rt), st, mx, q0.W1->map128,
-                    q0.W2->map128, q1.W1->map128, q1.W2->map128, a));
-    else
-      CK(launch_pdl(k_ffn_swap<1>, grid, dim3(SwapCfg<1>::THREADS), SwapCfg<1>::smem_bytes(rt), st, mx, q0.W1->map128,
-                    q0.W2->map128, q1.W1->map128, q1.W2->map128, a));
+    auto kern = mode == LADIFF_MODE_BF16X3 ? (c.att ? k_ffn_swap<2, true> : k_ffn_swap<2, false>)
+                                           : (c.att ? k_ffn_swap<1, true> : k_ffn_swap<1, false>);
+    const int smem = mode == LADIFF_MODE_BF16X3 ? SwapCfg<2>::smem_bytes(rt) : SwapCfg<1>::smem_bytes(rt);
+    CK(launch_pdl(kern, grid, dim3(SwapCfg<2>::THREADS), smem, st, mx, q0.W1->map128, q0.W2->map128, q1.W1->map128,
+                  q1.W2->map128, a));
     h->launches++;
     return LADIFF_OK;
   }
@@ -1324,8 +1323,10 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(1));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<2>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<1>::SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<1>::smem_bytes(48));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<1>::smem_bytes(48));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<1>::smem_bytes(48));
   if (e == cudaSuccess) e = set_tc_attr<256, 2>();
   if (e == cudaSuccess) e = set_tc_attr<256, 1>();
   if (e == cudaSuccess) e = set_tc_attr<128, 2>();
