@@ -61,6 +61,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// cluster barrier without release / acquire fences: pure control dependency (what it orders was observed through an mbarrier)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void st_cluster_v4u(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -372,14 +377,22 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         if (tc::elect_one()) issue_load(next_load);
         __syncwarp();
       }
-      tc::cluster_sync();  // #1
+      cluster_sync_relaxed();  // #1
       tc::cluster_sync();  // #2
       if (pr + 1 < p.npairs) tc::cluster_sync();  // #3
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
     const uint32_t idesc = tc::idesc_bf16_f32(128, rt);
+#ifdef EXP_UNIFORM_DESC
+    // operands of the issue loop through a lane-0 broadcast: provably warp-uniform -> descriptor arithmetic on the uniform datapath
+    const uint32_t ring_u = __shfl_sync(0xffffffffu, tc::smem_u32(ring), 0), xop_u = __shfl_sync(0xffffffffu, tc::smem_u32(xop), 0),
+                   hr_u = __shfl_sync(0xffffffffu, tc::smem_u32(hr), 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+#else
     const uint32_t ring_u = tc::smem_u32(ring), xop_u = tc::smem_u32(xop), hr_u = tc::smem_u32(hr);
+    const uint32_t tmem_u = tmem_base;
+#endif
     if (ATT) {
       tc::cluster_sync();  // #0
       fence_proxy_async_all();
@@ -402,7 +415,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           if (r == 0) SSTAMP(2 + 20 * pr);
           if (r == 8) SSTAMP(3 + 20 * pr);
         }
-        const uint32_t d = tmem_base + (ph ? 2 * rt : 0) + g * rt;
+        const uint32_t d = tmem_u + (ph ? 2 * rt : 0) + g * rt;
         const uint32_t sw = ring_u + slot * STG;
         const uint32_t sx = (ph ? hr_u : xop_u) + kb * NSPLIT * XT;
         if (tc::elect_one()) {
@@ -427,7 +440,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         __syncwarp();
       }
       if (lane == 0) SSTAMP(4 + 20 * pr);
-      tc::cluster_sync();  // #1
+      cluster_sync_relaxed();  // #1
       tc::cluster_sync();  // #2
       if (pr + 1 < p.npairs) {
         tc::cluster_sync();  // #3: the next X operand has been written by the owners (generic proxy, remote CTAs)
@@ -542,7 +555,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       tc::mbar_wait(accb, par);
       tc::tc_fence_after();
       if (e == 0 && lane == 0) SSTAMP(10 + 20 * pr);
-      tc::cluster_sync();  // #1: every CTA has retired its phase-B MMAs -> the h region is free to receive
+      cluster_sync_relaxed();  // #1: every CTA has retired its phase-B MMAs -> the h region is free to receive
       if (e == 0 && lane == 0) SSTAMP(11 + 20 * pr);
       {
         const uint32_t mine = (rank * tpc * C::D + f) * 4;
