@@ -344,6 +344,18 @@ def run_own(args):
         fl_b = sum(algorithmic_flops(lb))
         extra["batch1024"] = {"value": Bb / (ms_b / 1e3), "unit": "seq/s", "ms": ms_b,
                               "roofline_frac": fl_b / (ms_b / 1e3) / 1e12 / peaks["bf16_sustained"]}
+        # BASELINE configs 2 / 3, ragged variants (lengths = 4 * U[10,50), seed 1234): decode only and full sampling
+        import numpy as np
+        lr = [int(x) for x in (np.random.default_rng(1234).integers(10, 50, size=B) * 4)]
+        zr = model._diffusion_reverse(text_d, lr, latents=noise_d)
+        den_r, dec_r = algorithmic_flops(lr)
+        ms_dr = t_ms(lambda: model.vae.decode(zr, lr))
+        ms_sr = t_ms(lambda: model.vae.decode(model._diffusion_reverse(text_d, lr, latents=noise_d), lr))
+        extra["ragged"] = {"lengths": "4*U[10,50) seed 1234 (mean %.1f frames)" % (sum(lr) / len(lr)),
+                           "decode_only_ms": ms_dr, "decode_only_seq_s": B / (ms_dr / 1e3),
+                           "decode_only_tflops": dec_r / (ms_dr / 1e3) / 1e12,
+                           "sampling_ms": ms_sr, "sampling_seq_s": B / (ms_sr / 1e3),
+                           "sampling_tflops": (den_r + dec_r) / (ms_sr / 1e3) / 1e12}
         # CLIP, timed separately
         texts = [""] * B + [f"a person walks forward then turns {i}" for i in range(B)]
         model.text_encoder(texts); torch.cuda.synchronize()

@@ -271,12 +271,12 @@ int launch_tc(H* h, cudaStream_t st, const LinCall& c, const LinArgs& a, int til
     case EPI_RES: return launch_tc_e<BN, NS, EPI_RES>(h, st, c, a, tiles_m);
     case EPI_SILU: return launch_tc_e<BN, NS, EPI_SILU>(h, st, c, a, tiles_m);
     case EPI_LN:
-      if (BN == 256 && c.out.ld % 8 == 0 && !c.row_map && tiles_m * LN_CL <= 2 * 148 && !getenv("LADIFF_NO_CLUSTER"))
+      if (BN == 256 && c.out.ld % 8 == 0 && !c.row_map && (tiles_m * LN_CL <= 2 * 148 || getenv("LADIFF_LN_CLUSTER_ALL")) && !getenv("LADIFF_NO_CLUSTER"))
         return launch_tc_ln<NS, EPI_LN>(h, st, c, a, tiles_m);
       if (BN == 256) return launch_tc_e<256, NS, EPI_LN>(h, st, c, a, tiles_m);
       break;
     case EPI_LN_MOD_SILU:
-      if (BN == 256 && c.out.ld % 8 == 0 && !c.row_map && tiles_m * LN_CL <= 2 * 148 && !getenv("LADIFF_NO_CLUSTER"))
+      if (BN == 256 && c.out.ld % 8 == 0 && !c.row_map && (tiles_m * LN_CL <= 2 * 148 || getenv("LADIFF_LN_CLUSTER_ALL")) && !getenv("LADIFF_NO_CLUSTER"))
         return launch_tc_ln<NS, EPI_LN_MOD_SILU>(h, st, c, a, tiles_m);
       if (BN == 256) return launch_tc_e<256, NS, EPI_LN_MOD_SILU>(h, st, c, a, tiles_m);
       break;
