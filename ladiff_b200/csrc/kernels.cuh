@@ -219,8 +219,9 @@ __device__ __forceinline__ unsigned long long ktimer() {
 #define DQ_LD 1536    // q | k | 4 x v'
 #define DQX_LD 1792   // ... | X : row pitch of the in-projection buffer
 #define DC_LD 1280    // conditioning-token table row per layer: k | 4 x v'
-template <int MAXT>
-__global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx, const int* __restrict__ off, int S,
+// SEQS sequences per CTA (256 threads each, independent named barriers): SEQS = 2 halves the grid to <= 148 CTAs at B = 128
+template <int MAXT, int SEQS>
+__global__ void __launch_bounds__(256 * SEQS) k_attn_ln(const float* __restrict__ qkvx, const int* __restrict__ off, int S,
                                                  const float* __restrict__ textkv, int ld_textkv,
                                                  const float* __restrict__ timekv, const float* __restrict__ res, int ld_res,
                                                  const float* __restrict__ bo, const float* __restrict__ g,
@@ -228,21 +229,26 @@ __global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx,
                                                  unsigned long long* trace) {
   if (trace && threadIdx.x == 0) atomicMin(trace, ktimer());
   constexpr int NK = MAXT + 2;
-  __shared__ float Qs[MAXT][256];
-  __shared__ float Ks[NK][256];
-  __shared__ float Ps[MAXT][4][NK];
-  __shared__ float red[2][8][MAXT];
-  const int s = blockIdx.x;
+  __shared__ float Qs_[SEQS][MAXT][256];
+  __shared__ float Ks_[SEQS][NK][256];
+  __shared__ float Ps_[SEQS][MAXT][4][NK];
+  __shared__ float red_[SEQS][2][8][MAXT];
+  const int half = SEQS > 1 ? threadIdx.x >> 8 : 0, tid = threadIdx.x & 255;
+  float (*Qs)[256] = Qs_[half];
+  float (*Ks)[256] = Ks_[half];
+  float (*Ps)[4][NK] = Ps_[half];
+  float (*red)[8][MAXT] = red_[half];
+  const int s = blockIdx.x * SEQS + half;
   // the row offsets and the per-column vectors are written once per call, long before the previous grid: load them BEFORE the
   // dependency wait (a dependent global round trip costs ~1.8 us on the critical path of every layer otherwise)
   const int r0 = s < S ? __ldg(off + s) : 0, m = s < S ? min(__ldg(off + s + 1) - r0, MAXT) : 0;
-  const float boc = __ldg(bo + threadIdx.x), gc = __ldg(g + threadIdx.x), bc = __ldg(b + threadIdx.x);
+  const float boc = __ldg(bo + tid), gc = __ldg(g + tid), bc = __ldg(b + tid);
   pdl_prologue();
-  if (trace && threadIdx.x == 0) atomicMin(trace + 1, ~ktimer());
+  if (trace && tid == 0) atomicMin(trace + 1, ~ktimer());
   if (s >= S) return;
   if (m <= 0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = threadIdx.x;  // this thread's output column
+  const int warp = tid >> 5, lane = tid & 31;
+  const int c = tid;  // this thread's output column
   const float* tk = textkv + static_cast<long>(s) * ld_textkv;
   // ---- all global loads up front (one memory round trip): k rows -> smem, v' and the residual -> registers, q -> smem
   float v[4][NK], xr[MAXT];
@@ -265,10 +271,10 @@ __global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx,
     }
     Qs[i][c] = q * 0.125f;  // 1/sqrt(64) on q, like nn.MultiheadAttention
   }
-  __syncthreads();
-  if (trace && threadIdx.x == 0) atomicMin(trace + 2, ~ktimer());
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  if (trace && tid == 0) atomicMin(trace + 2, ~ktimer());
   // ---- scores: element e = (i, h, j); the 64-dim dot product walks d rotated by the lane to avoid bank conflicts
-  for (int e = threadIdx.x; e < m * 4 * NK; e += 256) {
+  for (int e = tid; e < m * 4 * NK; e += 256) {
     const int j = e % NK, h = (e / NK) & 3, i = e / (4 * NK);
     float sc = -INFINITY;
     if (j < m || j >= MAXT) {
@@ -287,9 +293,9 @@ __global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx,
     }
     Ps[i][h][j] = sc;
   }
-  __syncthreads();
-  if (threadIdx.x < m * 4) {
-    const int i = threadIdx.x >> 2, h = threadIdx.x & 3;
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  if (tid < m * 4) {
+    const int i = tid >> 2, h = tid & 3;
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < NK; ++j) mx = fmaxf(mx, Ps[i][h][j]);
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx,
 #pragma unroll
     for (int j = 0; j < NK; ++j) Ps[i][h][j] = pj[j] * inv;
   }
-  __syncthreads();
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
   // ---- out[i, c] = sum_h sum_j P[i][h][j] v'[h][j][c]  + out_proj bias + residual
   float acc[MAXT];
 #pragma unroll
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx,
     const float w = warp_sum(i < m ? acc[i] : 0.f);
     if (lane == 0) red[0][warp][i] = w;
   }
-  __syncthreads();
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
   float mean[MAXT];
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx,
     const float w = warp_sum(i < m ? dx * dx : 0.f);
     if (lane == 0) red[1][warp][i] = w;
   }
-  __syncthreads();
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
     if (i < m) {
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(256) k_attn_ln(const float* __restrict__ qkvx,
       (void)o;
     }
   }
-  if (trace && threadIdx.x == 0) atomicMin(trace + 3, ~ktimer());
+  if (trace && tid == 0) atomicMin(trace + 3, ~ktimer());
 }
 
 // Final LayerNorm (encoder.norm) + CFG combine + DDIM step + next-step input, one warp per (prompt, latent row):

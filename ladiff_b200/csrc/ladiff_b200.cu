@@ -937,11 +937,16 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   }
   if (fuse_att) {
     // attention + out-proj + residual + LN run as the prologue of the FFN kernel (one launch per layer after the in-projection)
-  } else if (p->T <= 5)
-    LAUNCHP(k_attn_ln<5>, S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
+  } else if (p->T <= 5) {
+    if (S > 148 && S <= 296 && getenv("LADIFF_ATTN_2SEQ")) {   // two sequences per CTA: one wave of <= 148 CTAs
+      LAUNCHP((k_attn_ln<5, 2>), (S + 1) / 2, 512, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
-  else
-    LAUNCHP(k_attn_ln<8>, S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
+    } else {
+      LAUNCHP((k_attn_ln<5, 1>), S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
+           p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
+    }
+  } else
+    LAUNCHP((k_attn_ln<8, 1>), S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
   if (mode != LADIFF_MODE_FP32 && ffn_cluster_enabled()) {
     // both feed-forward pairs of the layer in ONE cluster kernel: x1 -> x3 (fp32 + planes) -> s (planes); h never leaves the SM
