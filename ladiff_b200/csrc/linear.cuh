@@ -247,6 +247,29 @@ __device__ __forceinline__ void warp_load_rows(float (*tile)[36], const float* _
   __syncwarp();
 }
 
+// The same load in two halves, so that the global round trip of chunk c + 1 overlaps the arithmetic of chunk c (and, for the
+// first chunk, the mainloop): issue() only requests the 8 float4 per lane, finish() transposes them through the warp tile.
+__device__ __forceinline__ void warp_load_issue(float4 (&a)[8], const float* __restrict__ base, long ld, long row_base, int nvalid,
+                                                int col0, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr < nvalid) a[i] = *reinterpret_cast<const float4*>(base + (row_base + rr) * ld + col0 + (lane & 7) * 4);
+  }
+}
+__device__ __forceinline__ void warp_load_finish(float (*tile)[36], const float4 (&a)[8], int lane, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&tile[i * 4 + (lane >> 3)][(lane & 7) * 4]) = a[i];
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(&tile[lane][4 * q]);
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+  __syncwarp();
+}
+
 // Warp-cooperative, coalesced store of 32 finished rows x 32 cols (thread <-> row) through the warp-private tile.
 // Every store instruction writes whole 128-byte lines (fp32) / whole 32-byte sectors (bf16 planes).
 __device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs& p, long row_base, int nvalid, int col0,
@@ -453,6 +476,10 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const long drow = (valid && p.row_map) ? p.row_map[row] : row;
     float* xs = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);  // [2 passes][2 halves][128 rows] LayerNorm partials
     asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    // residual of the first LayerNorm chunk: requested while the mainloop runs
+    float4 rpre[8];
+    const bool ln_res = LN && EPI == EPI_LN && p.res != nullptr;
+    if (ln_res) warp_load_issue(rpre, p.res, p.ldres, row_base, nvalid, ch * 32, lane);
     // (2) accumulator ready
     tc::mbar_wait(accum_full, 0);
     tc::tc_fence_after();
@@ -468,14 +495,17 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float s = 0.f;
 #pragma unroll 1
       for (int c = ch; c < BN / 32; c += 2) {
-        if (EPI == EPI_LN && p.res) warp_load_rows(tile, p.res, p.ldres, nullptr, row_base, nvalid, c * 32, lane, t);
+        if (ln_res) {
+          warp_load_finish(tile, rpre, lane, t);
+          if (c + 2 < BN / 32) warp_load_issue(rpre, p.res, p.ldres, row_base, nvalid, (c + 2) * 32, lane);   // next chunk in flight
+        }
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 b4 = *reinterpret_cast<const float4*>(vec + c * 32 + 4 * q);
           v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
         }
-        if (EPI == EPI_LN && p.res) {
+        if (ln_res) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += t[j];
         }
