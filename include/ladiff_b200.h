@@ -138,10 +138,11 @@ LADIFF_API int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const fl
 LADIFF_API int ladiff_linear_bench(ladiff_handle* h, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t mode,
                         int32_t iters, float* ms_per_launch_host, void* stream);
 
-/* Test / measurement hook for the cluster-fused feed-forward kernel (csrc/ffn_cluster.cuh): runs the two feed-forward pairs of
- * denoiser layer `layer` (reference: mdiff_transformer.py:60-62 sa_block FFN + norm2, :248-262 FFN + StylizationBlock prologue)
- * on M rows x_dev[M,256] with the finalised denoiser weights; mod_dev = [scale(256) | shift(256)].  fused = 1: one cluster
- * kernel; fused = 0: the four separate fused linears.  Writes x3 and s ([M,256] fp32).  iters > 0: also returns the average
+/* Test / measurement hook for the cluster-fused feed-forward kernels (csrc/ffn_swap.cuh, csrc/ffn_cluster.cuh): runs the two
+ * feed-forward pairs of denoiser layer `layer` (reference: mdiff_transformer.py:60-62 sa_block FFN + norm2, :248-262 FFN +
+ * StylizationBlock prologue) on M rows x_dev[M,256] with the finalised denoiser weights; mod_dev = [scale(256) | shift(256)].
+ * fused = 1: the fused kernel the plans pick (token-group kernel k_ffn_swap for M <= 1776, else the 128-row cluster kernel);
+ * fused = 2: force the 128-row cluster kernel; fused = 0: the four separate fused linears.  Writes x3 and s ([M,256] fp32).  iters > 0: also returns the average
  * milliseconds of `iters` back-to-back calls (CUDA events on `stream`). */
 LADIFF_API int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t layer, const float* mod_dev, int32_t mode,
                     int32_t fused, int32_t iters, float* x3_out_dev, float* s_out_dev, float* ms_per_call_host, void* stream);
