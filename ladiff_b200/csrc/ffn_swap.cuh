@@ -642,18 +642,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           split2_bf16(y[4 * j], y[4 * j + 1], hi2[j].x, lo2[j].x);
           split2_bf16(y[4 * j + 2], y[4 * j + 3], hi2[j].y, lo2[j].y);
         }
-        if (ovalid) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (o.f32) *reinterpret_cast<float4*>(o.f32 + orow * o.ld + c0 + 64 * j) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-            if (o.pl && p.out_planes > 0) {
-              __nv_bfloat16* dh = o.pl + orow * o.ld + c0 + 64 * j;
-              *reinterpret_cast<uint2*>(dh) = hi2[j];
-              if (p.out_planes > 1) *reinterpret_cast<uint2*>(dh + static_cast<long>(o.rows_alloc) * o.ld) = lo2[j];
-            }
-          }
-        }
-        if (e == 0 && lane == 0) SSTAMP(18 + 20 * pr);
+        // the exchange first: it is on the critical path of the next pair, the global stores are not
         if (!last && own) {
           // next X operand into every CTA of the cluster: k-block j, 8 bytes inside swizzle chunk (c0 >> 3)
           const uint32_t rowoff = (otcl >> 3) * 1024 + (otcl & 7) * 128 + ((((c0 >> 3) ^ (otcl & 7)) << 4) | ((c0 & 7) * 2));
@@ -667,11 +656,23 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             }
           }
         }
-      }
-      if (e == 0 && lane == 0) SSTAMP(16 + 20 * pr);
-      if (!last) {
-        fence_proxy_async_all();
-        tc::cluster_sync();  // #3
+        if (e == 0 && lane == 0) SSTAMP(16 + 20 * pr);
+        if (!last) {
+          fence_proxy_async_all();
+          tc::cluster_sync();  // #3
+        }
+        if (ovalid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (o.f32) *reinterpret_cast<float4*>(o.f32 + orow * o.ld + c0 + 64 * j) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            if (o.pl && p.out_planes > 0) {
+              __nv_bfloat16* dh = o.pl + orow * o.ld + c0 + 64 * j;
+              *reinterpret_cast<uint2*>(dh) = hi2[j];
+              if (p.out_planes > 1) *reinterpret_cast<uint2*>(dh + static_cast<long>(o.rows_alloc) * o.ld) = lo2[j];
+            }
+          }
+        }
+        if (e == 0 && lane == 0) SSTAMP(18 + 20 * pr);
       }
       if (e == 0 && lane == 0) SSTAMP(17 + 20 * pr);
     }
