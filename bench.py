@@ -33,6 +33,26 @@ NFEATS = 263
 NCU_DRAM_BYTES = {"k_ffn_swap<2>": 7174912, "k_ffn_cluster<2>": 7165952}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 def lin(i, o):
     return 2.0 * i * o
 
@@ -133,6 +153,10 @@ def run_reference(args):
     import torch
     from oracle import ladiff_oracle as O
     torch.set_grad_enabled(False)
+    try:   # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and gets all host threads
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     cores = torch.get_num_threads()
     sd = O.make_state_dict(1234, NFEATS, perturb=False)
     text, noise, lengths = O.synthetic_inputs(B_PER_GPU, seed=1234, ragged=False, fixed_len=FRAMES)
@@ -143,7 +167,7 @@ def run_reference(args):
     sec = sum(times) / len(times)
     val = B_PER_GPU / sec
     sample = f"B={B_PER_GPU} L={FRAMES}: {den_steps} of {STEPS_DDIM} CFG denoiser steps timed and scaled x{STEPS_DDIM // den_steps} + one full decode, fp32 torch CPU"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "motion sequences/sec (50-step DDIM+CFG, 196 frames)", "value": val, "unit": "seq/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -363,6 +387,10 @@ def run_own(args):
         extra["clip_ms"] = (time.perf_counter() - t0) * 1e3
         # CPU baseline: the reference path (oracle port) on this box's host cores, bounded sample
         from oracle import ladiff_oracle as O
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))     # all host threads, whatever OMP_NUM_THREADS the launcher exported
+        except Exception:
+            pass
         sd = O.make_state_dict(1234, NFEATS, perturb=False)
         ctext, cnoise, clen = O.synthetic_inputs(B, seed=1234, ragged=False, fixed_len=FRAMES)
         cpu_reference_step(O, sd, ctext, cnoise, clen, 1)
@@ -410,7 +438,7 @@ def run_own(args):
                      "of the ncu --set full capture in profiles/r01h_ncu_full_layer_kernels.txt"),
             "path": path}
     out.update(extra)
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -426,6 +454,7 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="time one batch at a time instead of LADIFF.sample_stream")
     ap.add_argument("--quick", action="store_true", help="skip the extra measurements (kernel table, other modes, CPU baseline)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
