@@ -174,3 +174,22 @@ def test_bench_flop_model_matches_survey():
     assert sum(lengths) == 16092                                             # SURVEY.md 8d seeded ragged batch
     d2, e2 = bench.algorithmic_flops(lengths)
     assert abs((d2 + e2) / 1e12 - 1.376) < 0.002
+
+
+def test_bench_algorithmic_flops_match_survey():
+    """bench.py's roofline numerator is the SURVEY.md 8d contract figure: 27.03-27.07 MFLOP per valid latent row and step,
+    13.53 + 3.84 = 17.38 GFLOP per prompt at 196 frames, 2.224 TFLOP per batch of 128; seeded ragged batch 1.376 TFLOP."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    den, dec = bench.algorithmic_flops([196])
+    assert abs(den / 1e9 - 13.53) < 0.01 and abs(dec / 1e9 - 3.844) < 0.005
+    assert abs((den + dec) * 128 / 1e12 - 2.224) < 0.002
+    den1, _ = bench.algorithmic_flops([40], n_steps=1)           # m = 1: one valid row per CFG half
+    assert abs(den1 / 2 / 1e6 - 27.03) < 0.01
+    lengths = (np.random.default_rng(1234).integers(10, 50, size=128) * 4).tolist()
+    assert sum(lengths) == 16092                                   # SURVEY.md 8d: seeded ragged batch
+    d, c = bench.algorithmic_flops(lengths)
+    assert abs((d + c) / 1e12 - 1.376) < 0.002 and abs(c / 1e12 - 0.307) < 0.002
