@@ -384,15 +384,8 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
     const uint32_t idesc = tc::idesc_bf16_f32(128, rt);
-#ifdef EXP_UNIFORM_DESC
-    // operands of the issue loop through a lane-0 broadcast: provably warp-uniform -> descriptor arithmetic on the uniform datapath
-    const uint32_t ring_u = __shfl_sync(0xffffffffu, tc::smem_u32(ring), 0), xop_u = __shfl_sync(0xffffffffu, tc::smem_u32(xop), 0),
-                   hr_u = __shfl_sync(0xffffffffu, tc::smem_u32(hr), 0);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-#else
     const uint32_t ring_u = tc::smem_u32(ring), xop_u = tc::smem_u32(xop), hr_u = tc::smem_u32(hr);
     const uint32_t tmem_u = tmem_base;
-#endif
     if (ATT) {
       tc::cluster_sync();  // #0
       fence_proxy_async_all();
