@@ -100,6 +100,22 @@ LADIFF_API int ladiff_diffusion_reverse(ladiff_handle* h, const float* text_emb_
                              const int32_t* timesteps_host, const float* c1_host, const float* c2_host,
                              float guidance_scale, int32_t mode, float* z_out_dev, void* stream);
 
+/* Extended form of the loop for the reference's other scheduler / branch on this path:
+ *   - DDPM sampling (configs/modules/scheduler.yaml:16-29, diffusers DDPMScheduler.step): x' = c1*x + c2*eps + c3*noise,
+ *     c3_host[n_steps] = sqrt(variance_t) (NULL = all zero).  noise: step_noise_dev [n_steps,B,T,256] when injected
+ *     (parity tests; the reference draws torch.randn inside scheduler.step), else an in-kernel Philox4x32-10 stream
+ *     that is a pure function of (seed, step, element);
+ *   - ARDIFF autoregressive branch (ladiff.py:419-467): flags & LADIFF_REVERSE_AR -> only latent slot 0 of every
+ *     sequence is denoised, slots 1..rows-1 of noise_dev are fixed context latents (enclat, ladiff_denoiser.py:247-248),
+ *     rows_host[B] = 1 + number of context latents (no length mask on this branch: lengths_host may be NULL).
+ *   rows_host (optional) overrides m_i = ceil(L_i / frame_per_latent). */
+#define LADIFF_REVERSE_AR 1
+LADIFF_API int ladiff_diffusion_reverse_ex(ladiff_handle* h, const float* text_emb_dev, const int32_t* lengths_host,
+                                const int32_t* rows_host, int32_t B, const float* noise_dev, int32_t n_steps,
+                                const int32_t* timesteps_host, const float* c1_host, const float* c2_host,
+                                const float* c3_host, const float* step_noise_dev, uint64_t seed, int32_t flags,
+                                float guidance_scale, int32_t mode, float* z_out_dev, void* stream);
+
 /* LADiffDenoiser.forward (models/architectures/ladiff_denoiser.py:153-295), one call.
  *   sample_dev [S,T,256], timestep (integer), text_emb_dev [S,768], max_iter_elements_host [S]
  *   out_dev    [S,T,256]; rows t >= max_iter_elements[s] are written as 0 (the reference leaves

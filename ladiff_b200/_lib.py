@@ -48,6 +48,8 @@ def load_library() -> C.CDLL:
     lib.ladiff_set_weight.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32, vp]
     lib.ladiff_finalize_weights.argtypes = [vp, i32, vp]
     lib.ladiff_diffusion_reverse.argtypes = [vp, vp, pi32, i32, vp, i32, pi32, pf32, pf32, f32, i32, vp, vp]
+    lib.ladiff_diffusion_reverse_ex.argtypes = [vp, vp, pi32, pi32, i32, vp, i32, pi32, pf32, pf32, pf32, vp, C.c_uint64, i32, f32,
+                                                i32, vp, vp]
     lib.ladiff_denoiser_forward.argtypes = [vp, vp, i32, vp, pi32, i32, i32, vp, vp]
     lib.ladiff_cfg_ddim_step.argtypes = [vp, vp, vp, i32, f32, f32, f32, vp]
     lib.ladiff_vae_decode.argtypes = [vp, vp, pi32, i32, i32, i32, vp, vp]
@@ -60,7 +62,7 @@ def load_library() -> C.CDLL:
     lib.ladiff_last_launch_count.argtypes = [vp]
     lib.ladiff_last_launch_count.restype = i64
     for fn in ("ladiff_create", "ladiff_set_weight", "ladiff_finalize_weights", "ladiff_diffusion_reverse",
-               "ladiff_denoiser_forward", "ladiff_cfg_ddim_step", "ladiff_vae_decode", "ladiff_feats2joints",
+               "ladiff_diffusion_reverse_ex", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step", "ladiff_vae_decode", "ladiff_feats2joints",
                "ladiff_linear_test", "ladiff_linear_bench"):
         getattr(lib, fn).restype = C.c_int
     _lib = lib
@@ -68,7 +70,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("ladiff_abi_version", "ladiff_create", "ladiff_destroy", "ladiff_last_error", "ladiff_set_weight",
-           "ladiff_finalize_weights", "ladiff_diffusion_reverse", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step",
+           "ladiff_finalize_weights", "ladiff_diffusion_reverse", "ladiff_diffusion_reverse_ex", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step",
            "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_ffn_test", "ladiff_trace_read",
            "ladiff_last_launch_count")
 
@@ -156,19 +158,33 @@ class Engine:
         self._finalized |= which
 
     # -- compute ----------------------------------------------------------------------------------
-    def diffusion_reverse(self, text_emb: torch.Tensor, lengths: Sequence[int], noise: torch.Tensor,
+    def diffusion_reverse(self, text_emb: torch.Tensor, lengths: Optional[Sequence[int]], noise: torch.Tensor,
                           timesteps: Sequence[int], c1: Sequence[float], c2: Sequence[float], guidance_scale: float,
-                          mode: int) -> torch.Tensor:
-        B = len(lengths)
+                          mode: int, c3: Optional[Sequence[float]] = None, step_noise: Optional[torch.Tensor] = None,
+                          seed: int = 0, rows: Optional[Sequence[int]] = None, autoregressive: bool = False) -> torch.Tensor:
+        """The whole reverse loop (ladiff_diffusion_reverse[_ex]).  c3 / step_noise / seed: DDPM variance term (x' = c1 x +
+        c2 eps + c3 noise; noise injected [n,B,T,256] or Philox(seed)); rows / autoregressive: the ARDIFF branch."""
+        B = len(lengths) if lengths is not None else len(rows)
         text = _dev32(text_emb, "encoder_hidden_states").reshape(2 * B, -1)
         noise = _dev32(noise, "latents")
         if tuple(noise.shape) != (B, self.max_it, 256):
             raise ValueError(f"initial latents must be [{B},{self.max_it},256], got {tuple(noise.shape)}")
         z = torch.empty((self.max_it, B, 256), device=self.device, dtype=torch.float32)
         n = len(timesteps)
-        self._check(self.lib.ladiff_diffusion_reverse(self._h, _ptr(text), _i32(lengths), B, _ptr(noise), n,
-                                                      _i32(timesteps), _f32(c1), _f32(c2), float(guidance_scale),
-                                                      mode, _ptr(z), _stream()), "diffusion_reverse")
+        if c3 is None and step_noise is None and rows is None and not autoregressive:
+            self._check(self.lib.ladiff_diffusion_reverse(self._h, _ptr(text), _i32(lengths), B, _ptr(noise), n,
+                                                          _i32(timesteps), _f32(c1), _f32(c2), float(guidance_scale),
+                                                          mode, _ptr(z), _stream()), "diffusion_reverse")
+            return z
+        if step_noise is not None:
+            step_noise = _dev32(step_noise, "step_noise")
+            if tuple(step_noise.shape) != (n, B, self.max_it, 256):
+                raise ValueError(f"step noise must be [{n},{B},{self.max_it},256], got {tuple(step_noise.shape)}")
+        self._check(self.lib.ladiff_diffusion_reverse_ex(
+            self._h, _ptr(text), _i32(lengths) if lengths is not None else None, _i32(rows) if rows is not None else None, B,
+            _ptr(noise), n, _i32(timesteps), _f32(c1), _f32(c2), _f32(c3) if c3 is not None else None, _ptr(step_noise),
+            C.c_uint64(int(seed) & (2 ** 64 - 1)), 1 if autoregressive else 0, float(guidance_scale), mode, _ptr(z), _stream()),
+            "diffusion_reverse_ex")
         return z
 
     def denoiser_forward(self, sample: torch.Tensor, timestep: int, text_emb: torch.Tensor,

@@ -167,12 +167,23 @@ class EngineBound(nn.Module):
         from ._lib import MODES
         return MODES[self.precision]
 
+    def mark_dirty(self):
+        """Force a re-pack of the CUDA engine's weights at the next call (after out-of-band parameter surgery)."""
+        self._dirty = True
+
+    def _param_signature(self):
+        """(storage address, in-place version counter) of every parameter: ``p.data.copy_()``, an optimizer step or EMA
+        bump ``_version``; ``.to()`` / re-assignment change ``data_ptr`` -- a handful of integer reads per call."""
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def engine(self):
         from ._lib import Engine
         if self._engine is None:
             self._engine = Engine(**self._engine_kwargs)
-        if self._dirty:
+        sig = self._param_signature()
+        if self._dirty or sig != getattr(self, "_packed_sig", None):
             self._engine.set_weights(self.state_dict(), self._prefix)
             self._engine.finalize(self._which)
             self._dirty = False
+            self._packed_sig = sig
         return self._engine

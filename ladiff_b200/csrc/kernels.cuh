@@ -359,9 +359,40 @@ __global__ void __launch_bounds__(256 * SEQS) k_attn_ln(const float* __restrict_
 // Final LayerNorm (encoder.norm) + CFG combine + DDIM step + next-step input, one warp per (prompt, latent row):
 //   eps = LN(tok_u) + g (LN(tok_c) - LN(tok_u));  lat' = c1 lat + c2 eps   (models/modeltype/ladiff.py:487-492)
 //   x_next[row_u] = x_next[row_c] = lat' + pe[t]                           (ladiff.py:472-474 + ladiff_denoiser.py:251)
+// Philox4x32-10 counter-based generator + Box-Muller: the variance noise of the DDPM scheduler step (diffusers draws
+// torch.randn inside DDPMScheduler.step; here the stream is a pure function of (seed, step, element) so a captured graph
+// replays with fresh noise by bumping the seed in device memory).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  const float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+// One scheduler step of the reverse loop, fused with what surrounds it (ladiff.py:487-492 + encoder.norm of
+// ladiff_denoiser.py + query_pos of the next step): final LayerNorm of both CFG halves, eps = u + g (c - u),
+// x' = c1 x + c2 eps + c3 noise, next input x' + pe (fp32 + bf16 planes).  coef = {c1, c2, c3, guidance} of this step (device
+// table).  c3 != 0 (DDPM variance term): noise = (*noise_pp)[step] when a tensor was injected, else Philox(seed, step, element).
+// flags & 1 (ARDIFF, ladiff.py:419-467): only latent slot 0 is being denoised, slots >= 1 are fixed context latents.
+// elem0 / n_elem: offset of this chain's latents inside the call's [Btot, T, 256] tensor and its size (noise addressing).
 __global__ void k_cfg_ddim(const float* __restrict__ tok, const int* __restrict__ off, int B, int T,
                            const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ coef,
-                           float guidance, float* __restrict__ lat, const float* __restrict__ pe, Act x, int planes) {
+                           float* __restrict__ lat, const float* __restrict__ pe, Act x, int planes, int flags, int step,
+                           const float* const* __restrict__ noise_pp, const unsigned long long* __restrict__ seed_p,
+                           long elem0, long n_elem) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int bi = gw / T, t = gw % T;
   // row offsets: written once per call, long before the previous grid -> loaded before the dependency wait
@@ -393,7 +424,10 @@ __global__ void k_cfg_ddim(const float* __restrict__ tok, const int* __restrict_
   }
   const float ru_ = 1.0f / sqrtf(warp_sum(qu) * (1.f / 256.f) + LD_EPS);
   const float rc_ = 1.0f / sqrtf(warp_sum(qc) * (1.f / 256.f) + LD_EPS);
-  const float c1 = coef[0], c2 = coef[1];
+  const float c1 = coef[0], c2 = coef[1], c3 = coef[2], guidance = coef[3];
+  const bool frozen = (flags & 1) && t > 0;
+  const float* nz = (c3 != 0.f && noise_pp) ? *noise_pp : nullptr;
+  const unsigned long long seed = (c3 != 0.f && !nz && seed_p) ? *seed_p : 0ull;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = lane + 32 * j;
@@ -401,8 +435,24 @@ __global__ void k_cfg_ddim(const float* __restrict__ tok, const int* __restrict_
     const float ec = (c[j] - mc) * rc_ * g[col] + b[col];
     const float eps = eu + guidance * (ec - eu);
     const long li = (static_cast<long>(bi) * T + t) * 256 + col;
-    const float nl = c1 * lat[li] + c2 * eps;
-    lat[li] = nl;
+    float nl = lat[li];
+    if (!frozen) {
+      nl = c1 * nl + c2 * eps;
+      if (c3 != 0.f) {
+        float zn;
+        if (nz) {
+          zn = nz[static_cast<long>(step) * n_elem + elem0 + li];
+        } else {   // one Philox block per element pair; element e uses half (e & 1) of block e >> 1
+          const long e = elem0 + li;
+          const uint4 r4 = philox4x32_10(make_uint4(static_cast<uint32_t>(e >> 1), static_cast<uint32_t>(e >> 33), static_cast<uint32_t>(step), 0x4C414466u),
+                                         make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+          const float2 n2 = box_muller(r4.x, r4.y);
+          zn = (e & 1) ? n2.y : n2.x;
+        }
+        nl = fmaf(c3, zn, nl);
+      }
+      lat[li] = nl;
+    }
     const float xn = nl + pe[t * 256 + col];
     act_store(x, planes, ru, col, xn);
     act_store(x, planes, rc, col, xn);

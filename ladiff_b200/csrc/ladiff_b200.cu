@@ -140,6 +140,7 @@ struct ladiff_handle {
   std::map<std::string, std::unique_ptr<DenoisePlan>> den_plans;
   std::map<std::string, std::unique_ptr<ReversePlan>> rev_plans;
   std::map<std::string, std::unique_ptr<DecodePlan>> dec_plans;
+  uint64_t use_clock = 0;   // LRU stamp of the plan caches
   cudaStream_t cap_stream = nullptr;
   // LADIFF_TRACE=1: per-launch %globaltimer records of the fused linears (ladiff_trace_read)
   unsigned long long* trace = nullptr;
@@ -769,9 +770,13 @@ struct DenoisePlan {
   int planes = 0;  // bf16 planes written by producers: 0 fp32 mode, 1 bf16, 2 bf16x3
   // meta
   int *cnt = nullptr, *off = nullptr, *R = nullptr, *row_seq = nullptr, *row_t = nullptr, *ts = nullptr;
-  float* coef = nullptr;  // [n][2]
+  float* coef = nullptr;  // [n][4]: c1, c2, c3 (variance-noise coefficient, 0 for DDIM eta = 0), guidance
   std::vector<int> cached_ts;
   std::vector<float> cached_coef;
+  // scheduler-step extras shared by all chains of a ReversePlan (device scalars so that one captured graph serves every call)
+  const float** noise_pp = nullptr;        // injected per-step variance noise [n, Btot, T, 256], or *noise_pp == null -> Philox
+  unsigned long long* seed_p = nullptr;    // Philox seed
+  int ar_mode = 0;                         // ARDIFF: only latent slot 0 is denoised
   // inputs staged in the workspace so the captured graph has fixed addresses
   float *text768 = nullptr, *lat = nullptr;
   // time side
@@ -787,6 +792,7 @@ struct DenoisePlan {
   const float* text_src = nullptr;  // parent text [2*Btot,768]; this chain covers prompts [b0, b0+B)
   int text_Btot = 0, b0 = 0, chain = 0;
   const int* cnt_src = nullptr;     // parent m[Btot] + b0
+  uint64_t last_use = 0;
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
   ~DenoisePlan() {
@@ -806,6 +812,9 @@ struct ReversePlan {
   std::vector<std::unique_ptr<DenoisePlan>> chains;
   std::vector<int> cached_ts;
   std::vector<float> cached_coef;
+  const float** noise_pp = nullptr;
+  unsigned long long* seed_p = nullptr;
+  uint64_t last_use = 0;
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
   ~ReversePlan() {
@@ -840,7 +849,7 @@ int build_denoise_plan(H* h, DenoisePlan* p, int S, int n, int mode, bool cfg, f
     p->mod = tables->mod;
   } else {
     CK(ar.alloc((void**)&p->ts, n * sizeof(int)));
-    CK(ar.alloc((void**)&p->coef, 2 * n * sizeof(float)));
+    CK(ar.alloc((void**)&p->coef, 4 * n * sizeof(float)));
     CKS(alloc_act(h, ar, &p->sin, n, 768, f, tcm));
     CKS(alloc_act(h, ar, &p->t1, n, 256, f, tcm));
     CKS(alloc_act(h, ar, &p->temb, n, 256, true, tcm));
@@ -1022,20 +1031,21 @@ int enqueue_meta(H* h, cudaStream_t st, const int* cnt_host, int S, int* cnt, in
   return LADIFF_OK;
 }
 
-int enqueue_reverse_body(H* h, DenoisePlan* p, cudaStream_t st, float guidance) {
+int enqueue_reverse_body(H* h, DenoisePlan* p, cudaStream_t st) {
   CKS(enqueue_text_tables(h, p, st));
   LAUNCHP(k_pack_x, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, p->lat, p->B, p->T, h->den_pe, p->row_seq, p->row_t, p->R,
          p->xin.act, p->planes);
   for (int step = 0; step < p->n; ++step) {
     CKS(enqueue_den_tokens(h, p, st, step));
     LAUNCHP(k_cfg_ddim, cdiv(static_cast<long>(p->B) * p->T * 32, 256), 256, 0, st, p->xa.act.f32, p->off, p->B, p->T, h->den_fg, h->den_fb,
-           p->coef + 2 * step, guidance, p->lat, h->den_pe, p->xin.act, p->planes);
+           p->coef + 4 * step, p->lat, h->den_pe, p->xin.act, p->planes, p->ar_mode, step, p->noise_pp, p->seed_p,
+           static_cast<long>(p->b0) * p->T * 256, static_cast<long>(p->text_Btot) * p->T * 256);
   }
   return LADIFF_OK;
 }
 
 // all chains of a ReversePlan: chain 0 on `st`, the others on forked side streams joined back into `st`
-int enqueue_reverse_chains(H* h, ReversePlan* rp, cudaStream_t st, float guidance) {
+int enqueue_reverse_chains(H* h, ReversePlan* rp, cudaStream_t st) {
   const int nch = static_cast<int>(rp->chains.size());
   if (nch > 1) {
     if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -1052,7 +1062,7 @@ int enqueue_reverse_chains(H* h, ReversePlan* rp, cudaStream_t st, float guidanc
     }
     LAUNCH(k_scan_counts, 1, 1024, 0, sc, p->cnt_src, p->S, p->B, p->off, p->R);
     LAUNCH(k_fill_rows, cdiv(static_cast<long>(p->S) * 32, 256), 256, 0, sc, p->off, p->S, p->row_seq, p->row_t, (int*)nullptr, 0);
-    CKS(enqueue_reverse_body(h, p, sc, guidance));
+    CKS(enqueue_reverse_body(h, p, sc));
     if (c > 0) {
       CK(cudaEventRecord(h->ev_join[c], sc));
       CK(cudaStreamWaitEvent(st, h->ev_join[c], 0));
@@ -1073,12 +1083,16 @@ int pick_chains(int B) {
   return n < 1 ? 1 : (n > 4 ? 4 : n);
 }
 
-int build_reverse_plan(H* h, ReversePlan* rp, int B, int n, int mode) {
+int build_reverse_plan(H* h, ReversePlan* rp, int B, int n, int mode, int ar_flag) {
   rp->B = B;
   rp->n = n;
   rp->mode = mode;
   const int T = h->cfg.max_it;
   CK(rp->ar.alloc((void**)&rp->cnt, B * sizeof(int)));
+  CK(rp->ar.alloc((void**)&rp->noise_pp, sizeof(float*)));
+  CK(rp->ar.alloc((void**)&rp->seed_p, sizeof(unsigned long long)));
+  CK(cudaMemset(rp->noise_pp, 0, sizeof(float*)));
+  CK(cudaMemset(rp->seed_p, 0, sizeof(unsigned long long)));
   CK(rp->ar.alloc((void**)&rp->text768, static_cast<size_t>(2 * B) * 768 * sizeof(float)));
   CK(rp->ar.alloc((void**)&rp->lat, static_cast<size_t>(B) * T * 256 * sizeof(float)));
   const int nch = pick_chains(B);
@@ -1092,6 +1106,9 @@ int build_reverse_plan(H* h, ReversePlan* rp, int B, int n, int mode) {
     p->b0 = b0;
     p->cnt_src = rp->cnt + b0;
     p->chain = c;
+    p->noise_pp = rp->noise_pp;
+    p->seed_p = rp->seed_p;
+    p->ar_mode = ar_flag;
     rp->chains.push_back(std::move(p));
   }
   return LADIFF_OK;
@@ -1107,6 +1124,7 @@ struct DecodePlan {
   float* z = nullptr;  // staged [T,B,256]
   ActBuf zrows, x0, xa, xb, x1, x2, skip[4], a, hbuf, xn;
   float *qkv = nullptr, *q2 = nullptr, *memkv = nullptr;
+  uint64_t last_use = 0;
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
   ~DecodePlan() {
@@ -1269,6 +1287,21 @@ cudaError_t set_tc_attr() {
   return e;
 }
 
+// Plan caches are bounded: a plan owns its workspace and CUDA graph (the hoisted delta table alone is ~118 MB at B = 128 x 50
+// steps), so a sweep over batch sizes / step counts must not grow device memory without limit.  Least recently used first.
+constexpr size_t MAX_PLANS = 6;
+template <class P>
+void evict_lru(std::map<std::string, std::unique_ptr<P>>& m, const std::string& keep) {
+  while (m.size() > MAX_PLANS) {
+    auto victim = m.end();
+    for (auto it = m.begin(); it != m.end(); ++it)
+      if (it->first != keep && it->second && (victim == m.end() || it->second->last_use < victim->second->last_use)) victim = it;
+    if (victim == m.end()) break;
+    cudaDeviceSynchronize();   // the victim's graph / workspace may still be in flight on some stream
+    m.erase(victim);
+  }
+}
+
 int check_mode(H* h, int mode) {
   if (mode < 0 || mode > 2) return h->err.set(LADIFF_ERR_INVALID, "unknown mode %d", mode);
   return LADIFF_OK;
@@ -1423,58 +1456,81 @@ int ladiff_finalize_weights(ladiff_handle* h, int32_t which, void* stream) {
 int ladiff_diffusion_reverse(ladiff_handle* h, const float* text_emb_dev, const int32_t* lengths_host, int32_t B,
                              const float* noise_dev, int32_t n_steps, const int32_t* timesteps_host, const float* c1_host,
                              const float* c2_host, float guidance_scale, int32_t mode, float* z_out_dev, void* stream) {
+  return ladiff_diffusion_reverse_ex(h, text_emb_dev, lengths_host, nullptr, B, noise_dev, n_steps, timesteps_host, c1_host, c2_host,
+                                     nullptr, nullptr, 0ull, 0, guidance_scale, mode, z_out_dev, stream);
+}
+
+int ladiff_diffusion_reverse_ex(ladiff_handle* h, const float* text_emb_dev, const int32_t* lengths_host,
+                                const int32_t* rows_host, int32_t B, const float* noise_dev, int32_t n_steps,
+                                const int32_t* timesteps_host, const float* c1_host, const float* c2_host, const float* c3_host,
+                                const float* step_noise_dev, uint64_t seed, int32_t flags, float guidance_scale, int32_t mode,
+                                float* z_out_dev, void* stream) {
   if (!h) return LADIFF_ERR_INVALID;
   h->launches = 0;
   h->trace_n = 0;
   if (!h->den_ready) return h->err.set(LADIFF_ERR_STATE, "denoiser weights not finalised");
   CKS(check_mode(h, mode));
-  if (!text_emb_dev || !lengths_host || !noise_dev || !timesteps_host || !c1_host || !c2_host || !z_out_dev || B < 1 || n_steps < 1)
+  if (!text_emb_dev || (!lengths_host && !rows_host) || !noise_dev || !timesteps_host || !c1_host || !c2_host || !z_out_dev || B < 1 ||
+      n_steps < 1 || (flags & ~1))
     return h->err.set(LADIFF_ERR_INVALID, "ladiff_diffusion_reverse: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int T = h->cfg.max_it;
-  uint32_t gbits;
-  memcpy(&gbits, &guidance_scale, 4);
+  const int ar_flag = flags & LADIFF_REVERSE_AR;
   char key[96];
-  snprintf(key, sizeof(key), "cfg:%d:%d:%d:%08x", B, n_steps, mode, gbits);
+  snprintf(key, sizeof(key), "cfg:%d:%d:%d:%d", B, n_steps, mode, ar_flag);   // guidance / coefficients / seed live in device tables
   auto& slot = h->rev_plans[key];
   if (!slot) {
     slot.reset(new ReversePlan());
-    int s = build_reverse_plan(h, slot.get(), B, n_steps, mode);
+    int s = build_reverse_plan(h, slot.get(), B, n_steps, mode, ar_flag);
     if (s != LADIFF_OK) {
       h->rev_plans.erase(key);
       return s;
     }
+    evict_lru(h->rev_plans, key);
   }
-  ReversePlan* rp = slot.get();
+  ReversePlan* rp = h->rev_plans[key].get();
+  rp->last_use = ++h->use_clock;
   // ---- per-call inputs staged at fixed addresses (the captured graph reads them); the ragged row layout is derived on
   // the device inside the graph
   std::vector<int> cnt(B);
   for (int b = 0; b < B; ++b) {
-    if (lengths_host[b] < 1) return h->err.set(LADIFF_ERR_INVALID, "lengths[%d] = %d", b, lengths_host[b]);
-    int m = (lengths_host[b] + h->cfg.frame_per_latent - 1) / h->cfg.frame_per_latent;
+    int m;
+    if (rows_host) {   // explicit latent rows per sequence (ARDIFF: 1 + number of context latents, no length mask)
+      m = rows_host[b];
+      if (m < 1 || m > T) return h->err.set(LADIFF_ERR_INVALID, "rows[%d] = %d outside [1, %d]", b, m, T);
+    } else {
+      if (lengths_host[b] < 1) return h->err.set(LADIFF_ERR_INVALID, "lengths[%d] = %d", b, lengths_host[b]);
+      m = (lengths_host[b] + h->cfg.frame_per_latent - 1) / h->cfg.frame_per_latent;
+    }
     cnt[b] = m < T ? m : T;
   }
   CK(cudaMemcpyAsync(rp->cnt, cnt.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(rp->text768, text_emb_dev, static_cast<size_t>(2 * B) * 768 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(rp->lat, noise_dev, static_cast<size_t>(B) * T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(rp->noise_pp, &step_noise_dev, sizeof(float*), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(rp->seed_p, &seed, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
   // ---- schedule-dependent tables (cached; shared by all chains)
   std::vector<int> ts(timesteps_host, timesteps_host + n_steps);
-  std::vector<float> coef(2 * n_steps);
+  std::vector<float> coef(4 * n_steps);
   for (int i = 0; i < n_steps; ++i) {
-    coef[2 * i] = c1_host[i];
-    coef[2 * i + 1] = c2_host[i];
+    coef[4 * i] = c1_host[i];
+    coef[4 * i + 1] = c2_host[i];
+    coef[4 * i + 2] = c3_host ? c3_host[i] : 0.f;
+    coef[4 * i + 3] = guidance_scale;
   }
-  if (ts != rp->cached_ts || coef != rp->cached_coef) {
-    DenoisePlan* p0 = rp->chains[0].get();
-    CK(cudaDeviceSynchronize());  // previous users of the tables (any stream)
+  DenoisePlan* p0 = rp->chains[0].get();
+  if (coef != rp->cached_coef) {   // stream-ordered: earlier replays on this stream have read the old values by then
+    CK(cudaMemcpyAsync(p0->coef, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    rp->cached_coef = coef;
+  }
+  if (ts != rp->cached_ts) {
+    CK(cudaDeviceSynchronize());  // previous users of the time tables (any stream)
     CK(cudaMemcpyAsync(p0->ts, ts.data(), n_steps * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(p0->coef, coef.data(), 2 * n_steps * sizeof(float), cudaMemcpyHostToDevice, st));
     CKS(enqueue_time_tables(h, p0, st));
     CK(cudaStreamSynchronize(st));
     rp->cached_ts = ts;
-    rp->cached_coef = coef;
   }
-  CKS(run_graphed(h, st, &rp->exec, &rp->graph_launches, [&](cudaStream_t s) { return enqueue_reverse_chains(h, rp, s, guidance_scale); }));
+  CKS(run_graphed(h, st, &rp->exec, &rp->graph_launches, [&](cudaStream_t s) { return enqueue_reverse_chains(h, rp, s); }));
   LAUNCH(k_z_out, cdiv(static_cast<long>(B) * T * 256, 256), 256, 0, st, rp->lat, rp->cnt, B, T, z_out_dev);
   return LADIFF_OK;
 }
@@ -1499,8 +1555,10 @@ int ladiff_denoiser_forward(ladiff_handle* h, const float* sample_dev, int32_t t
       h->den_plans.erase(key);
       return s;
     }
+    evict_lru(h->den_plans, key);
   }
-  DenoisePlan* p = slot.get();
+  DenoisePlan* p = h->den_plans[key].get();
+  p->last_use = ++h->use_clock;
   std::vector<int> cnt(S);
   for (int s = 0; s < S; ++s) {
     if (max_iter_elements_host[s] < 1) return h->err.set(LADIFF_ERR_INVALID, "max_iter_elements[%d] = %d", s, max_iter_elements_host[s]);
@@ -1557,8 +1615,10 @@ int ladiff_vae_decode(ladiff_handle* h, const float* z_dev, const int32_t* lengt
       h->dec_plans.erase(key);
       return s;
     }
+    evict_lru(h->dec_plans, key);
   }
-  DecodePlan* p = slot.get();
+  DecodePlan* p = h->dec_plans[key].get();
+  p->last_use = ++h->use_clock;
   CKS(enqueue_meta(h, st, cnt.data(), B, p->cnt, p->foff, p->Rf, p->frow_seq, p->frow_t, p->frow_dst, max_len));
   CKS(enqueue_meta(h, st, mcnt.data(), B, p->mcnt, p->moff, p->Rm, p->mrow_seq, p->mrow_t, nullptr, 0));
   CK(cudaMemcpyAsync(p->z, z_dev, static_cast<size_t>(T) * B * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));

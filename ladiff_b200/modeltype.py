@@ -41,10 +41,14 @@ class LADIFF(nn.Module):
         self.joint_distro_fix = abl.get("JOINT_DISTRO_FIX", False)
         self.ARDIFF = cfg.get("ARDIFF", False)
         self.LAD = abl.get("LAD", True)
-        if cfg.get("IDEA", "ard") != "ard" or self.ARDIFF or not self.LAD or self.joint_distro_fix or self.test_efficiency:
-            raise NotImplementedError("ladiff_b200 implements the LADiff sampling configuration: IDEA 'ard', ARDIFF False, "
+        if cfg.get("IDEA", "ard") != "ard" or not self.LAD or self.joint_distro_fix or self.test_efficiency:
+            raise NotImplementedError("ladiff_b200 implements the LADiff sampling configurations: IDEA 'ard', ARDIFF False / True, "
                                       "LAD True, JOINT_DISTRO_FIX False, TEST_EFFICIENCY False "
                                       "(configs/config_ladiff_humanml3d.yaml:18-19,58-64)")
+        self.motion_conditioning = cfg.model.get("motion_conditioning", "last")      # ARDIFF only (reference :52)
+        nf = cfg.TRAIN.get("N_FRAMES", "None")
+        self.nframes = None if nf in ("None", None) else nf                            # reference :58,63
+        self.latent_dim_stage1 = cfg.model.get("latent_dim_stage1", None)
         if self.condition not in ("text", "text_uncond"):
             raise NotImplementedError("text-conditioned sampling only")
         try:
@@ -70,7 +74,8 @@ class LADIFF(nn.Module):
         """denoiser + VAE (+ feats2joints) share one library handle: one workspace, one stream of work."""
         if self._shared_engine is None:
             from ._lib import Engine
-            self._shared_engine = Engine(nfeats=self.nfeats, max_it=self.max_it, frame_per_latent=self.frame_per_latent)
+            self._shared_engine = Engine(nfeats=self.nfeats, max_it=self.max_it, frame_per_latent=self.frame_per_latent,
+                                         max_frames=getattr(self.vae, "max_frames", 196))
             self.denoiser.bind_engine(self._shared_engine)
             self.vae.bind_engine(self._shared_engine)
             if hasattr(self.datamodule, "bind_engine"):
@@ -123,7 +128,7 @@ class LADIFF(nn.Module):
 
     @torch.no_grad()
     def _diffusion_reverse(self, encoder_hidden_states, lengths=None, latents: Optional[torch.Tensor] = None,
-                           generator: Optional[torch.Generator] = None):
+                           generator: Optional[torch.Generator] = None, step_noise: Optional[torch.Tensor] = None):
         """encoder_hidden_states [2B,1,768] (uncond rows first), lengths List[int] -> latents [MAX_IT, B, 256] with rows
         >= ceil(L/48) exactly zero (reference :333-571, LAD branch).  ``latents=`` / ``generator=`` inject the initial noise
         the reference draws from the global RNG (:380-385)."""
@@ -139,26 +144,81 @@ class LADIFF(nn.Module):
             guidance = 1.0
         if len(lengths) != bsz:
             raise ValueError(f"{len(lengths)} lengths for {bsz} prompts")
-        if latents is None:
-            latents = torch.randn((bsz, self.max_it, self.latent_dim[-1]), device=encoder_hidden_states.device,
-                                  dtype=torch.float, generator=generator)
-        latents = latents * self.scheduler.init_noise_sigma                     # :407 (masked rows are never read)
         self.scheduler.set_timesteps(self.cfg.model.scheduler.num_inference_timesteps)   # :410
         eta = 0.0
         if "eta" in set(inspect.signature(self.scheduler.step).parameters.keys()):       # :415-417
             eta = self.cfg.model.scheduler.get("eta", 0.0)
         if not hasattr(self.scheduler, "fused_coefficients"):
-            raise NotImplementedError("the fused loop needs a scheduler exposing fused_coefficients() (DDIM, eta=0)")
-        ts, c1, c2 = self.scheduler.fused_coefficients(eta)
+            raise NotImplementedError("the fused loop needs a scheduler exposing fused_coefficients() (DDIM eta=0 / DDPM)")
+        coef = self.scheduler.fused_coefficients(eta)
+        ts, c1, c2 = coef[:3]
+        c3 = coef[3] if len(coef) > 3 else None                 # DDPM: variance-noise coefficient per step
         self.denoiser.engine()       # weight sync
-        return engine.diffusion_reverse(encoder_hidden_states, [int(x) for x in lengths], latents, ts, c1, c2,
-                                        guidance, self.denoiser.mode)
+        lengths = [int(x) for x in lengths]
+        extra = {}
+        if c3 is not None:
+            if step_noise is not None:
+                extra = dict(c3=c3, step_noise=step_noise)
+            else:   # the reference draws torch.randn inside scheduler.step; here: Philox stream seeded from torch's generator
+                self._noise_calls = getattr(self, "_noise_calls", 0) + 1
+                base = int(torch.randint(0, 2 ** 62, (1,)).item()) if generator is None else int(generator.initial_seed())
+                extra = dict(c3=c3, seed=base + 0x9E3779B97F4A7C15 * self._noise_calls)
+        if self.ARDIFF:
+            return self._reverse_autoregressive(engine, encoder_hidden_states, lengths, bsz, latents, generator, ts, c1, c2,
+                                                guidance, extra)
+        if latents is None:
+            latents = torch.randn((bsz, self.max_it, self.latent_dim[-1]), device=encoder_hidden_states.device,
+                                  dtype=torch.float, generator=generator)
+        latents = latents * self.scheduler.init_noise_sigma                     # :407 (masked rows are never read)
+        return engine.diffusion_reverse(encoder_hidden_states, lengths, latents, ts, c1, c2, guidance, self.denoiser.mode, **extra)
+
+    def _reverse_autoregressive(self, engine, text, lengths, bsz, latents, generator, ts, c1, c2, guidance, extra):
+        """ARDIFF branch (reference :360-365, :419-467, :562-570): latent slot k is denoised with the N-step loop conditioned on
+        the already-denoised slots (``enclat``: all of them for motion_conditioning 'full'/'middle', the last one for 'last');
+        every iteration is one C-ABI call -- the conditioning latents ride along as fixed rows of the token sequence
+        (ladiff_denoiser.py:247-248), no key-padding mask on this branch (max_iter_elements is not passed, :436-443)."""
+        unit = self.latent_dim_stage1 if self.nframes is not None else self.frame_per_latent          # :343-356
+        ar_iterations = -(-max(lengths) // int(unit))
+        if ar_iterations > self.max_it:
+            raise ValueError(f"{ar_iterations} autoregressive iterations exceed MAX_IT = {self.max_it}")
+        D = self.latent_dim[-1]
+        if latents is None:
+            latents = torch.randn((bsz, ar_iterations, D), device=text.device, dtype=torch.float, generator=generator)   # :360-365
+        if latents.shape[1] < ar_iterations:
+            raise ValueError(f"initial latents need {ar_iterations} slots, got {latents.shape[1]}")
+        latents = latents * self.scheduler.init_noise_sigma
+        final = torch.zeros((bsz, self.max_it, D), device=text.device, dtype=torch.float)
+        step_noise = extra.get("step_noise")
+        for k in range(ar_iterations):
+            if k == 0:
+                ctx = final[:, :0]
+            elif self.motion_conditioning in ("full", "middle"):
+                ctx = final[:, :k]
+            elif self.motion_conditioning == "last":
+                ctx = final[:, k - 1:k]
+            else:
+                raise ValueError(f"motion_conditioning {self.motion_conditioning!r}")
+            seq = torch.zeros((bsz, self.max_it, D), device=text.device, dtype=torch.float)
+            seq[:, 0] = latents[:, k]
+            seq[:, 1:1 + ctx.shape[1]] = ctx
+            ex = dict(extra)
+            if step_noise is not None:       # [ar_iterations, n, B, T, 256] when injected for the AR branch
+                ex["step_noise"] = step_noise[k]
+            elif "seed" in ex:
+                ex["seed"] = ex["seed"] + k
+            z = engine.diffusion_reverse(text, None, seq, ts, c1, c2, guidance, self.denoiser.mode,
+                                         rows=[1 + ctx.shape[1]] * bsz, autoregressive=True, **ex)
+            final[:, k] = z[0]
+        out = final.permute(1, 0, 2).contiguous()                               # :466 -> [MAX_IT (zero-padded, :567-569), B, 256]
+        for i, m in enumerate(max_iter_elements(lengths, self.frame_per_latent)):     # :562-566
+            out[m:, i] = 0
+        return out
 
     @torch.no_grad()
-    def sample_features(self, encoder_hidden_states, lengths, latents=None, generator=None):
-        """_diffusion_reverse + vae.decode without leaving the device: [B, max(lengths), nfeats] CUDA tensor."""
+    def sample_features(self, encoder_hidden_states, lengths, latents=None, generator=None, max_len=None):
+        """_diffusion_reverse + vae.decode without leaving the device: [B, max_len or max(lengths), nfeats] CUDA tensor."""
         z = self._diffusion_reverse(encoder_hidden_states, lengths, latents=latents, generator=generator)
-        return self.vae.decode(z, lengths)
+        return self.vae.decode(z, lengths, max_len=max_len)
 
     @torch.no_grad()
     def sample_stream(self, batches):

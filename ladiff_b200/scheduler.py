@@ -154,25 +154,53 @@ class DDPMScheduler(_Base):
         ts = ts.copy().astype(np.int64)
         self.timesteps = torch.from_numpy(ts).to(device) if device is not None else torch.from_numpy(ts)
 
+    def _alphas(self, t: int):
+        """(alpha_bar_t, alpha_bar_prev, alpha_t, beta_t) for the step t -> t - train/inference (== t - 1 at 1000 steps, the
+        only DDPM sampling configuration the reference's YAML lists, scheduler.yaml:16-29)."""
+        ratio = self.config.num_train_timesteps // (self.num_inference_steps or self.config.num_train_timesteps)
+        prev_t = t - ratio
+        a_t = self.alphas_cumprod[t].double().item()
+        a_p = self.alphas_cumprod[prev_t].double().item() if prev_t >= 0 else 1.0
+        cur_alpha = a_t / a_p
+        return a_t, a_p, cur_alpha, 1.0 - cur_alpha
+
     def _get_variance(self, t: int) -> float:
-        a_t = self.alphas_cumprod[t].item()
-        a_p = self.alphas_cumprod[t - 1].item() if t > 0 else 1.0
-        var = (1 - a_p) / (1 - a_t) * self.betas[t].item()
+        a_t, a_p, _, cur_beta = self._alphas(t)
+        var = (1 - a_p) / (1 - a_t) * cur_beta
         vt = self.config.variance_type
         if vt == "fixed_small":
             return max(var, 1e-20)
         if vt == "fixed_small_log":
-            return math.log(max(var, 1e-20))
+            return math.exp(0.5 * math.log(max(var, 1e-20))) ** 2
         if vt == "fixed_large":
-            return self.betas[t].item()
+            return cur_beta
         if vt == "fixed_large_log":
-            return math.log(self.betas[t].item())
+            return math.exp(0.5 * math.log(cur_beta)) ** 2
         raise ValueError(f"variance_type {vt} not supported")
 
-    def step(self, model_output, timestep, sample, generator=None, return_dict: bool = True, **kwargs):
+    def fused_coefficients(self, eta: float = 0.0) -> Tuple[List[int], List[float], List[float], List[float]]:
+        """(timesteps, c1, c2, c3) with  prev = c1 * sample + c2 * eps + c3 * noise  (epsilon prediction, no clipping):
+        x0 = (x - sqrt(1 - abar_t) eps) / sqrt(abar_t);  prev = k0 x0 + kt x + sqrt(var_t) noise  (Ho et al. 2020 eq. 7)."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if self.config.clip_sample or self.config.prediction_type != "epsilon":
+            raise ValueError("fused DDPM loop supports clip_sample=False, prediction_type='epsilon' "
+                             "(configs/modules/scheduler.yaml:16-29); use .step() for other settings")
+        ts, c1, c2, c3 = [], [], [], []
+        for t in self.timesteps.tolist():
+            t = int(t)
+            a_t, a_p, cur_alpha, cur_beta = self._alphas(t)
+            k0 = math.sqrt(a_p) * cur_beta / (1 - a_t)
+            kt = math.sqrt(cur_alpha) * (1 - a_p) / (1 - a_t)
+            ts.append(t)
+            c1.append(kt + k0 / math.sqrt(a_t))
+            c2.append(-k0 * math.sqrt(1 - a_t) / math.sqrt(a_t))
+            c3.append(math.sqrt(self._get_variance(t)) if t > 0 else 0.0)
+        return ts, c1, c2, c3
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict: bool = True, variance_noise=None, **kwargs):
         t = int(timestep)
-        a_t = self.alphas_cumprod[t].item()
-        a_p = self.alphas_cumprod[t - 1].item() if t > 0 else 1.0
+        a_t, a_p, cur_alpha, cur_beta = self._alphas(t)
         b_t, b_p = 1 - a_t, 1 - a_p
         if self.config.prediction_type == "epsilon":
             x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
@@ -182,11 +210,12 @@ class DDPMScheduler(_Base):
             raise ValueError(f"prediction_type given as {self.config.prediction_type} must be one of `epsilon`, `sample`")
         if self.config.clip_sample:
             x0 = x0.clamp(-1, 1)
-        c0 = (a_p ** 0.5 * self.betas[t].item()) / b_t
-        ct = self.alphas[t].item() ** 0.5 * b_p / b_t
+        c0 = (a_p ** 0.5 * cur_beta) / b_t
+        ct = cur_alpha ** 0.5 * b_p / b_t
         prev = c0 * x0 + ct * sample
         if t > 0:
-            noise = torch.randn(model_output.shape, generator=generator, device=model_output.device, dtype=model_output.dtype)
+            noise = variance_noise if variance_noise is not None else torch.randn(
+                model_output.shape, generator=generator, device=model_output.device, dtype=model_output.dtype)
             prev = prev + self._get_variance(t) ** 0.5 * noise
         out = SchedulerOutput(prev_sample=prev, pred_original_sample=x0)
         return out if return_dict else (prev,)

@@ -70,7 +70,15 @@ class MldTextEncoder(nn.Module):
             self.text_model.training = False
             for p in self.text_model.parameters():
                 p.requires_grad = False
+        self.finetune = bool(finetune)
         self._uncond = None
+        # the cached "" embedding is a function of the weights: drop it whenever they are (re)loaded
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_uncond", None))
+
+    def _cache_ok(self) -> bool:
+        """The reference re-encodes "" on every call (ladiff.py:259-265); the cache is exact only while the weights cannot
+        move: never with finetune=True or in training mode."""
+        return not self.finetune and not self.training
 
     def _apply(self, fn, *a, **k):
         self._uncond = None
@@ -88,13 +96,15 @@ class MldTextEncoder(nn.Module):
 
     def forward(self, texts: List[str]) -> torch.Tensor:
         """List[str] (length n) -> [n, 1, 768]  (reference :50-90, 'clip' branch :75-78)."""
+        if not self._cache_ok():
+            self._uncond = None
         uniq, index = [], {}
         for t in texts:
             if t not in index and not (t == "" and self._uncond is not None):
                 index[t] = len(uniq)
                 uniq.append(t)
         emb = self._encode(uniq) if uniq else None
-        if "" in index:
+        if "" in index and self._cache_ok():
             self._uncond = emb[index[""]].clone()
         rows = [self._uncond if (t == "" and t not in index) else emb[index[t]] for t in texts]
         return torch.stack(rows, 0).unsqueeze(1)

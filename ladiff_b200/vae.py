@@ -73,6 +73,7 @@ class LADiffVae(EngineBound):
         self.global_motion_token = nn.Parameter(torch.randn(self.max_it * 2, self.latent_dim))
         self.skel_embedding = nn.Linear(nfeats, self.latent_dim)
         self.final_layer = nn.Linear(self.latent_dim, nfeats)
+        self.max_frames = int(max_frames)
         self._init_engine_state(precision, dict(nfeats=nfeats, max_it=self.max_it, frame_per_latent=self.frame_per_latent,
                                                 max_frames=max_frames))
 
@@ -88,12 +89,14 @@ class LADiffVae(EngineBound):
         return masks
 
     @torch.no_grad()
-    def decode(self, z: Tensor, lengths: List[int], plot_att_map=None, latentwise_gen=None):
-        """z [MAX_IT, B, 256], lengths List[int] -> [B, max(lengths), nfeats]  (reference :288-362)."""
+    def decode(self, z: Tensor, lengths: List[int], plot_att_map=None, latentwise_gen=None, max_len: Optional[int] = None):
+        """z [MAX_IT, B, 256], lengths List[int] -> [B, max(lengths), nfeats]  (reference :288-362).
+        ``max_len`` (extension): pad to this many frames instead of ``max(lengths)`` -- sharded callers need one shape on
+        every rank before the all-gather (``parallel.gather_motions``)."""
         if plot_att_map is not None or latentwise_gen is not None:
             raise NotImplementedError("attention-map plotting / latent-wise generation are analysis tools outside the sampling path")
         lengths = [int(x) for x in lengths]
-        out = self.engine().vae_decode(z, lengths, self.mode)
+        out = self.engine().vae_decode(z, lengths, self.mode, max_len=max_len)
         return out.to(z.dtype)
 
     def encode(self, features: Tensor, lengths: Optional[List[int]] = None):

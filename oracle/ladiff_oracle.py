@@ -334,12 +334,23 @@ def skip_encoder_md(src: Tensor, xf: Tensor, emb: Tensor, P: SD, p: str, src_key
 
 
 def denoiser_forward(sd: SD, sample: Tensor, timestep: Tensor, encoder_hidden_states: Tensor,
-                     max_iter_elements: Tensor, trace: Optional[dict] = None) -> Tensor:
+                     max_iter_elements: Optional[Tensor], trace: Optional[dict] = None,
+                     enclat: Optional[Tensor] = None) -> Tensor:
     """LADiffDenoiser.forward, text condition / trans_enc / MD_TRANS:
     architectures/ladiff_denoiser.py:153-295.  sample [2B,T,256], timestep 0-dim,
-    encoder_hidden_states [2B,1,768] -> [2B,T,256]."""
-    latent_mask = latent_mask_of(max_iter_elements, sample.shape[1])                    # :164-171
+    encoder_hidden_states [2B,1,768] -> [2B,T,256].  ``enclat`` [2B,k,256] (ARDIFF conditioning latents, :218-219,
+    :247-248) is appended to the token sequence; that branch passes no max_iter_elements -> no key-padding mask (:252-255)."""
+    T_in = sample.shape[1]
+    n_tok = T_in + (enclat.shape[1] if enclat is not None else 0)
+    if max_iter_elements is not None:
+        latent_mask = latent_mask_of(max_iter_elements, n_tok)                          # :164-171
+    else:
+        latent_mask = torch.ones((sample.shape[0], n_tok), dtype=torch.bool)
     sample = sample.permute(1, 0, 2)                                                    # :175
+    if enclat is not None:
+        sample_in = torch.cat((sample, enclat.permute(1, 0, 2)), dim=0)                 # :219,248
+    else:
+        sample_in = sample
     timesteps = timestep.expand(sample.shape[1]).clone()                                # :184
     time_emb = timestep_embedding(timesteps).to(sample.dtype)                           # :185-186
     time_emb = F.linear(F.silu(F.linear(time_emb, sd["denoiser.time_embedding.linear_1.weight"],
@@ -349,7 +360,7 @@ def denoiser_forward(sd: SD, sample: Tensor, timestep: Tensor, encoder_hidden_st
     text_emb = encoder_hidden_states.permute(1, 0, 2)                                   # :193
     text_emb_latent = F.linear(F.relu(text_emb), sd["denoiser.emb_proj.1.weight"],
                                sd["denoiser.emb_proj.1.bias"])                          # :72-73,198
-    xseq = sample + sd["denoiser.query_pos.pe"][:sample.shape[0]]                       # :251
+    xseq = sample_in + sd["denoiser.query_pos.pe"][:sample_in.shape[0]]                 # :251
     tokens = skip_encoder_md(xseq, text_emb_latent, time_emb, sd, "denoiser.encoder", ~latent_mask, trace)
     return tokens[:sample.shape[0]].permute(1, 0, 2)                                    # :272,292
 
@@ -418,6 +429,28 @@ def ddim_step(eps: Tensor, t: int, sample: Tensor, acp: Tensor, n: int, num_trai
     return a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
 
 
+def ddpm_step(eps: Tensor, t: int, sample: Tensor, acp: Tensor, n: int, noise: Optional[Tensor],
+              num_train_timesteps: int = 1000) -> Tensor:
+    """diffusers DDPMScheduler.step, epsilon prediction, variance_type fixed_small, clip_sample false
+    (configs/modules/scheduler.yaml:16-29; Ho et al. 2020 eq. 7); ``noise`` is the variance noise the
+    scheduler draws itself.  Third-party: parity unpinned like DDIM."""
+    prev_t = t - num_train_timesteps // n
+    a_t = acp[t].double()
+    a_p = acp[prev_t].double() if prev_t >= 0 else torch.tensor(1.0, dtype=torch.float64)
+    cur_alpha = a_t / a_p
+    cur_beta = 1 - cur_alpha
+    x0 = (sample - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
+    prev = (a_p ** 0.5 * cur_beta / (1 - a_t)) * x0 + (cur_alpha ** 0.5 * (1 - a_p) / (1 - a_t)) * sample
+    if t > 0:
+        var = torch.clamp((1 - a_p) / (1 - a_t) * cur_beta, min=1e-20)
+        prev = prev + var ** 0.5 * noise
+    return prev.to(sample.dtype)
+
+
+def ddpm_timesteps(n: int, num_train_timesteps: int = 1000) -> np.ndarray:
+    return np.arange(0, num_train_timesteps, num_train_timesteps // n)[::-1].copy().astype(np.int64)
+
+
 # ---- the sampling loop -----------------------------------------------------
 def initial_latents(noise: Tensor, lengths: Sequence[int]) -> Tensor:
     """models/modeltype/ladiff.py:379-390,407: randn [B,5,256] (injected), rows >= m_i zeroed, x init_noise_sigma(=1)."""
@@ -430,14 +463,15 @@ def initial_latents(noise: Tensor, lengths: Sequence[int]) -> Tensor:
 
 def diffusion_reverse(sd: SD, encoder_hidden_states: Tensor, lengths: Sequence[int], noise: Tensor,
                       num_inference_steps: int = 50, guidance_scale: float = 7.5,
-                      record: Optional[dict] = None, denoiser_fn=None) -> Tensor:
+                      record: Optional[dict] = None, denoiser_fn=None, scheduler: str = "ddim",
+                      step_noise: Optional[Tensor] = None) -> Tensor:
     """LADIFF._diffusion_reverse, IDEA 'ard' / ARDIFF False / LAD branch:
     models/modeltype/ladiff.py:333-340,378-390,406-417,470-500,562-566.
     encoder_hidden_states [2B,1,768] (uncond rows first), noise [B,5,256] -> latents [5,B,256]."""
     mie = max_iter_elements_of(lengths)
     latents = initial_latents(noise, lengths)
     acp = ddim_alphas_cumprod()
-    ts = ddim_timesteps(num_inference_steps)
+    ts = ddim_timesteps(num_inference_steps) if scheduler == "ddim" else ddpm_timesteps(num_inference_steps)
     mie2 = torch.cat([mie] * 2)
     for i, t in enumerate(ts):
         x2 = torch.cat([latents] * 2)                                                   # :472-474
@@ -447,13 +481,88 @@ def diffusion_reverse(sd: SD, encoder_hidden_states: Tensor, lengths: Sequence[i
             noise_pred = denoiser_fn(x2, torch.tensor(int(t)), encoder_hidden_states, mie2)
         u, c = noise_pred.chunk(2)                                                      # :488
         noise_pred = u + guidance_scale * (c - u)                                       # :489-490
-        latents = ddim_step(noise_pred, int(t), latents, acp, num_inference_steps)      # :491-492
+        if scheduler == "ddim":
+            latents = ddim_step(noise_pred, int(t), latents, acp, num_inference_steps)  # :491-492
+        else:       # step_noise [n,B,5,256]: what DDPMScheduler.step would draw
+            latents = ddpm_step(noise_pred, int(t), latents, acp, num_inference_steps, step_noise[i])
         if record is not None and (i + 1) in record.get("steps", ()):
             record[f"latents_after_{i + 1}"] = latents.clone()
     latents = latents.permute(1, 0, 2)                                                  # :500
     for i, e in enumerate(mie):
         latents[int(e):, i] = 0                                                         # :564-566
     return latents
+
+
+def diffusion_reverse_ardiff(sd: SD, encoder_hidden_states: Tensor, lengths: Sequence[int], noise: Tensor,
+                             num_inference_steps: int = 50, guidance_scale: float = 7.5,
+                             motion_conditioning: str = "last", denoiser_fn=None) -> Tensor:
+    """LADIFF._diffusion_reverse, ARDIFF branch: models/modeltype/ladiff.py:343-365,419-467,562-570.
+    noise [B, ar_iterations, 256] -> latents [MAX_IT, B, 256]."""
+    ar_iterations = -(-max(lengths) // FRAME_PER_LATENT)                                # :349-356
+    acp = ddim_alphas_cumprod()
+    ts = ddim_timesteps(num_inference_steps)
+    final = None
+    for k in range(ar_iterations):
+        lat = noise[:, k:k + 1].clone()                                                 # :423
+        if k > 0:
+            enclat = final[:, :k] if motion_conditioning in ("full", "middle") else final[:, k - 1:k]   # :425-431
+            enclat = torch.cat([enclat] * 2)
+        else:
+            enclat = None
+        for t in ts:
+            x2 = torch.cat([lat] * 2)
+            if denoiser_fn is None:
+                pred = denoiser_forward(sd, x2, torch.tensor(int(t)), encoder_hidden_states, None, enclat=enclat)
+            else:
+                pred = denoiser_fn(x2, torch.tensor(int(t)), encoder_hidden_states, enclat)
+            u, c = pred.chunk(2)
+            lat = ddim_step(u + guidance_scale * (c - u), int(t), lat, acp, num_inference_steps)
+        final = lat if final is None else torch.cat((final, lat), dim=1)                # :462
+    latents = final.permute(1, 0, 2)                                                    # :466
+    for i, e in enumerate(max_iter_elements_of(lengths)):
+        latents[int(e):, i] = 0                                                         # :564-566
+    if latents.shape[0] < MAX_IT:                                                       # :567-569
+        latents = torch.cat((latents, torch.zeros((MAX_IT - latents.shape[0],) + tuple(latents.shape[1:]))), dim=0)
+    return latents
+
+
+# ---- LA-VAE encoder ("next" row f3) -------------------------------------------------
+def skip_encoder_plain(src: Tensor, P: SD, p: str, src_key_padding_mask: Tensor) -> Tensor:
+    """SkipTransformerEncoder.forward, non-MD branch: operator/cross_attention.py:48-67 with
+    TransformerEncoderLayer.forward_post (:293-307, gelu)."""
+    nb = (NUM_LAYERS - 1) // 2
+    x, xs = src, []
+    for i in range(nb):
+        x = encoder_layer_post(x, P, f"{p}.input_blocks.{i}", src_key_padding_mask, F.gelu)
+        xs.append(x)
+    x = encoder_layer_post(x, P, f"{p}.middle_block", src_key_padding_mask, F.gelu)
+    for i in range(nb):
+        x = torch.cat([x, xs.pop()], dim=-1)
+        x = F.linear(x, P[f"{p}.linear_blocks.{i}.weight"], P[f"{p}.linear_blocks.{i}.bias"])
+        x = encoder_layer_post(x, P, f"{p}.output_blocks.{i}", src_key_padding_mask, F.gelu)
+    return _ln(x, P, p + ".norm")
+
+
+def vae_encode(sd: SD, features: Tensor, lengths: Sequence[int], eps: Optional[Tensor] = None):
+    """LADiffVae.encode (LAD, JOINT_DISTRO_FIX false, MLP_DIST false): architectures/ladiff_vae.py:162-286.
+    features [B, max(lengths), nfeats] -> (latent [5,B,256], mu [5,B,256], std [5,B,256], max_iter_elements).
+    ``eps`` [5,B,256] is the standard-normal draw of ``dist.rsample()`` (latent = mu + std * eps)."""
+    bs = features.shape[0]
+    mask = lengths_to_mask(lengths, features.shape[1])                                  # :178
+    x = F.linear(features, sd["vae.skel_embedding.weight"], sd["vae.skel_embedding.bias"]).permute(1, 0, 2)   # :182-186
+    dist = torch.tile(sd["vae.global_motion_token"][:, None, :], (1, bs, 1))            # :189
+    mie = max_iter_elements_of(lengths)                                                 # :198
+    dm = latent_mask_of(mie, MAX_IT)
+    aug_mask = torch.cat((dm, dm, mask), 1)                                             # :203-210
+    xseq = torch.cat((dist, x), 0)                                                      # :213
+    xseq = xseq + sd["vae.query_pos_encoder.pe"][:xseq.shape[0]]                        # :220
+    out = skip_encoder_plain(xseq, sd, "vae.encoder", ~aug_mask)[:dist.shape[0]]        # :221-222
+    mu, logvar = out[:MAX_IT], out[MAX_IT:]                                             # :258-259
+    std = logvar.exp().pow(0.5)                                                         # :262
+    latent = mu + std * (eps if eps is not None else torch.randn(mu.shape))             # :263-264
+    for i, e in enumerate(mie):
+        latent[int(e):, i] = 0                                                          # :265-268
+    return latent, mu, std, mie
 
 
 def sample_motion(sd: SD, encoder_hidden_states: Tensor, lengths: Sequence[int], noise: Tensor,

@@ -84,6 +84,37 @@ def main():
     feats = vaek.decode(zin, lengths)
     np.savez_compressed(os.path.join(OUT, "decode_kit.npz"), weight_seed=seed, input_seed=17, lengths=lengths,
                         feats=feats.numpy())
+    # ---- 5. LADiffVae.encode: the deterministic part of the reference output (dist.loc / dist.scale) on ragged motions
+    lengths = [196, 44, 96, 145, 57]
+    g = torch.Generator().manual_seed(19)
+    motion = 0.5 * torch.randn((len(lengths), max(lengths), 263), generator=g)
+    for i, L in enumerate(lengths):
+        motion[i, L:] = 0
+    torch.manual_seed(0)
+    lat, dist, mie = vae.encode(motion, lengths)
+    np.savez_compressed(os.path.join(OUT, "encode.npz"), weight_seed=seed, input_seed=19, lengths=lengths,
+                        mu=dist.loc.numpy(), std=dist.scale.numpy(), mie=mie.numpy())
+
+    # ---- 6. one denoiser call on the ARDIFF branch (enclat conditioning, no key-padding mask: ladiff_denoiser.py:218-255)
+    g = torch.Generator().manual_seed(23)
+    Bq = 3
+    text = torch.randn((2 * Bq, 1, 768), generator=g)
+    xs = torch.randn((2 * Bq, 1, 256), generator=g)
+    enclat = torch.randn((2 * Bq, 2, 256), generator=g)
+    out = den(sample=xs, timestep=torch.tensor(441), encoder_hidden_states=text, enclat=enclat, lengths=None)[0]
+    np.savez_compressed(os.path.join(OUT, "denoiser_step_ardiff.npz"), weight_seed=seed, input_seed=23, timestep=441,
+                        out=out.numpy())
+
+    # ---- 7. recover_from_ric (data/humanml/scripts/motion_process.py:415-430), the reference's own function
+    import sys
+    sys.path.insert(0, R.REF_SRC)
+    from ladiff.data.humanml.scripts.motion_process import recover_from_ric
+    g = torch.Generator().manual_seed(29)
+    data = 0.3 * torch.randn((3, 40, 263), generator=g)
+    np.savez_compressed(os.path.join(OUT, "recover_from_ric.npz"), input_seed=29,
+                        joints22=recover_from_ric(data, 22).numpy(),
+                        joints21=recover_from_ric(data[..., :251], 21).numpy())
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

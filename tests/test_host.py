@@ -98,6 +98,12 @@ def test_mirror_modules_have_the_reference_key_layout(oracle_sd):
     den.load_state_dict(O.sub(oracle_sd, "denoiser."), strict=True)
     vae.load_state_dict(O.sub(oracle_sd, "vae."), strict=True)
     assert den._dirty and vae._dirty                       # engine weights re-packed on next use
+    # in-place parameter updates (optimizer step, EMA, p.data.copy_) are detected too: they move the signature the
+    # engine compares before every call (stale packed weights)
+    sig = den._param_signature()
+    with torch.no_grad():
+        den.encoder.norm.weight.mul_(1.0)
+    assert den._param_signature() != sig
     # the zero_module-d matrices are re-initialised (xavier) like SkipTransformerEncoder._reset_parameters does
     assert den.encoder.input_blocks[0].ffn.linear2.weight.abs().sum() > 0
     # encode (torch path, outside the CUDA hot path) runs on CPU
@@ -142,6 +148,14 @@ def test_text_encoder_dedup_and_shape():
     assert torch.equal(e2[0], e[0])
     with pytest.raises(FileNotFoundError):
         MldTextEncoder("/nonexistent/clip-vit-large-patch14")
+    # the cached "" embedding must not survive a weight (re)load, and is never used in training / finetune mode
+    enc.load_state_dict(enc.state_dict())
+    assert enc._uncond is None
+    enc(["", "x"])
+    assert enc._uncond is not None
+    enc.train()
+    enc(["", "x"])
+    assert enc._uncond is None
 
 
 def test_c_abi_library_exports_every_declared_symbol():
