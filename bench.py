@@ -7,6 +7,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W                       # one rank per GPU, weak scaling
 
+    python bench.py --sweep 8192 [--micro 128]                      # BASELINE config 5: N prompts sharded over the ranks (strong scaling)
+
 A "step" = one batch of 128 synthetic prompts (random-init weights, injected noise) through
 ``LADIFF._diffusion_reverse`` + ``vae.decode``.  CLIP is timed separately (``clip_ms``), as north_star asks.
 Prints ONE JSON line (rank 0).
@@ -29,8 +31,17 @@ GUIDANCE = 7.5
 NFEATS = 263
 
 
+METRIC = "motion sequences/sec (50-step DDIM+CFG, 196 frames)"
+
+
+def workload_config(batch=B_PER_GPU):
+    """The SAME config object in both arms (the driver compares them): what is computed, not how."""
+    return {"workload": f"LA-DDPM sampling batch {batch} per GPU, {STEPS_DDIM}-step DDIM + CFG {GUIDANCE}, {FRAMES} frames, + LA-VAE decode to {NFEATS}-d features",
+            "weights": "random-init (reference initialiser families), seed 1234", "precision": "fp32-grade (1e-3 max-abs parity contract on decoded features)"}
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_DRAM_BYTES = {"k_ffn_swap<2>": 7174912, "k_ffn_cluster<2>": 7165952}
+NCU_DRAM_BYTES = {"k_ffn_swap<2>": 7174912}
 
 
 _REAL_STDOUT = None
@@ -125,25 +136,13 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_step(O, sd, text, noise, lengths, den_steps):
-    """One bounded sample of the reference's CPU path (oracle restatement): `den_steps` of the 50 denoiser steps, scaled
-    linearly (every step is identical work), plus one full decode.  Returns seconds for the full 50-step workload."""
-    import torch
+def cpu_reference_run(O, sd, text, noise, lengths, den_steps=STEPS_DDIM):
+    """The reference's CPU path (oracle restatement, un-hoisted) on one batch: ALL `den_steps` CFG denoiser steps + DDIM + the
+    decode.  Returns (seconds, decoded features)."""
     t0 = time.perf_counter()
-    mie = O.max_iter_elements_of(lengths)
-    lat = O.initial_latents(noise, lengths)
-    acp = O.ddim_alphas_cumprod()
-    ts = O.ddim_timesteps(STEPS_DDIM)
-    mie2 = torch.cat([mie] * 2)
-    for t in ts[:den_steps]:
-        pred = O.denoiser_forward(sd, torch.cat([lat] * 2), torch.tensor(int(t)), text, mie2)
-        u, c = pred.chunk(2)
-        lat = O.ddim_step(u + GUIDANCE * (c - u), int(t), lat, acp, STEPS_DDIM)
-    t_den = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    O.vae_decode(sd, O.initial_latents(noise, lengths).permute(1, 0, 2).contiguous(), lengths)
-    t_dec = time.perf_counter() - t0
-    return t_den * (STEPS_DDIM / den_steps) + t_dec, t_den, t_dec
+    z = O.diffusion_reverse(sd, text, lengths, noise, den_steps, GUIDANCE)
+    feats = O.vae_decode(sd, z, lengths)
+    return time.perf_counter() - t0, feats
 
 
 def run_reference(args):
@@ -160,25 +159,28 @@ def run_reference(args):
     cores = torch.get_num_threads()
     sd = O.make_state_dict(1234, NFEATS, perturb=False)
     text, noise, lengths = O.synthetic_inputs(B_PER_GPU, seed=1234, ragged=False, fixed_len=FRAMES)
-    den_steps = 5
-    for _ in range(args.warmup):
-        cpu_reference_step(O, sd, text, noise, lengths, 1)
-    times = [cpu_reference_step(O, sd, text, noise, lengths, den_steps)[0] for _ in range(args.steps)]
+    for _ in range(max(1, args.warmup)):
+        cpu_reference_run(O, sd, text, noise, lengths, 2)                    # warm-up steps (threads, allocator): 2 denoiser steps each
+    times = [cpu_reference_run(O, sd, text, noise, lengths)[0] for _ in range(args.steps)]
+    times.sort()
     sec = sum(times) / len(times)
     val = B_PER_GPU / sec
-    sample = f"B={B_PER_GPU} L={FRAMES}: {den_steps} of {STEPS_DDIM} CFG denoiser steps timed and scaled x{STEPS_DDIM // den_steps} + one full decode, fp32 torch CPU"
+    sample = (f"B={B_PER_GPU} L={FRAMES}: every step runs all {STEPS_DDIM} CFG denoiser steps + DDIM + one full decode "
+              f"(nothing extrapolated), fp32 torch CPU, {cores} threads (oracle/ladiff_oracle.py)")
     emit(json.dumps({
-        "impl": "reference", "metric": "motion sequences/sec (50-step DDIM+CFG, 196 frames)", "value": val, "unit": "seq/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "seq/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"LA-DDPM sampling batch {B_PER_GPU}, {STEPS_DDIM}-step DDIM + CFG {GUIDANCE}, {FRAMES} frames, + LA-VAE decode; CPU"},
+        "config": workload_config(),
+        "p50_latency_ms": times[len(times) // 2] * 1e3,
         "cpu_baseline": {"value": val, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # --------------------------------------------------------------------------------------------------
-def run_own(args):
+def setup(args):
+    """One process per GPU: device, NCCL group (world > 1) and the model with random-init weights of the reference architecture."""
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -201,6 +203,88 @@ def run_own(args):
     torch.manual_seed(1234)                                  # configs/base.yaml:2 SEED_VALUE
     model = LADIFF(cfg, SyntheticDataModule(NFEATS, 22)).to(dev).eval()   # random-init weights of the reference architecture
     model.set_precision(args.mode)
+    return torch, dist, rank, world, local, dev, model
+
+
+def run_sweep(args):
+    """BASELINE config 5: N synthetic prompts sharded over the ranks (``parallel.shard_range``: contiguous, balanced), each rank
+    samples its shard in micro-batches through ``LADIFF.sample_stream`` (host inputs, pinned), and ONE all-gather
+    (``parallel.gather_motions``) returns every motion to every rank.  Strong scaling: total work fixed as the rank count grows.
+    Timed from the first H2D copy to the end of the all-gather, device events, max over ranks."""
+    torch, dist, rank, world, local, dev, model = setup(args)
+    from ladiff_b200.parallel import gather_motions, shard_range
+    N, micro = args.sweep, args.micro
+    s0, e0 = shard_range(N, rank, world)
+    n_local = e0 - s0
+    g = torch.Generator().manual_seed(1234 + rank)
+    nb = -(-n_local // micro)
+    sizes = [min(micro, n_local - i * micro) for i in range(nb)]
+    # one pinned micro-batch of prompts per distinct size, re-used (the content does not change the work)
+    host = {b: (torch.randn((2 * b, 1, 768), generator=g).pin_memory(), torch.randn((b, 5, 256), generator=g).pin_memory()) for b in set(sizes)}
+    local_out = torch.zeros((n_local, FRAMES, NFEATS), device=dev)
+
+    def batches():
+        for b in sizes:
+            t, nz = host[b]
+            yield t.to(dev, non_blocking=True), [FRAMES] * b, nz.to(dev, non_blocking=True)
+
+    def run():
+        i = 0
+        for feats in model.sample_stream(batches()):
+            local_out[i:i + feats.shape[0]].copy_(feats)
+            i += feats.shape[0]
+        return gather_motions(local_out, [FRAMES] * n_local, N, max_len=FRAMES)
+
+    for b in set(sizes):                                      # warm-up: plans / graphs of every micro-batch size, NCCL communicator
+        t, nz = host[b]
+        for _ in range(2):
+            model.vae.decode(model._diffusion_reverse(t.to(dev), [FRAMES] * b, latents=nz.to(dev)), [FRAMES] * b)
+    if world > 1:
+        dist.all_reduce(torch.zeros(1, device=dev))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    motions, lens = run()
+    eb.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ea.elapsed_time(eb)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ok = tuple(motions.shape) == (N, FRAMES, NFEATS) and len(lens) == N and bool(torch.isfinite(motions[::97]).all())
+    if rank == 0:
+        peaks = measured_peaks()
+        fl = sum(algorithmic_flops([FRAMES] * N))
+        emit(json.dumps({
+            "metric": METRIC, "value": N / (ms / 1e3), "unit": "seq/s", "n_gpus": world, "steps": nb, "warmup": 2,
+            "ms_per_step": ms / nb, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+            "config": {"workload": f"throughput sweep: {N} synthetic prompts sharded over {world} GPU(s), micro-batch {micro}, "
+                                   f"{STEPS_DDIM}-step DDIM + CFG {GUIDANCE}, {FRAMES} frames, decode to {NFEATS}-d, one all-gather of all motions"},
+            "sweep": {"prompts": N, "micro_batch": micro, "prompts_per_rank": n_local, "micro_batches_per_rank": nb, "total_ms": ms,
+                      "all_motions_on_every_rank": ok, "gathered_bytes": int(motions.numel() * 4)},
+            "e2e": {"value": N / (ms / 1e3), "unit": "seq/s", "h2d_bytes_per_step": int(micro * (2 * 768 + 5 * 256) * 4), "d2h_bytes_per_step": 0},
+            "roofline": {"bound": "tensor", "achieved": fl / (ms / 1e3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": fl / (ms / 1e3) / 1e12 / peaks["bf16_sustained"], "traffic": None, "scope": "whole sweep"},
+            "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_own(args):
+    torch, dist, rank, world, local, dev, model = setup(args)
+    import ladiff_b200 as L
+    from ladiff_b200.data import SyntheticDataModule
+    from ladiff_b200.modeltype import LADIFF
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     lengths = [FRAMES] * B
@@ -208,7 +292,7 @@ def run_own(args):
     noise_h = torch.randn((B, 5, 256), generator=g).pin_memory()
     text_d, noise_d = text_h.to(dev), noise_h.to(dev)
     out_h = torch.empty((B, FRAMES, NFEATS), dtype=torch.float32).pin_memory()
-    gather = [torch.empty((B, FRAMES, NFEATS), device=dev) for _ in range(world)] if world > 1 else None
+    gather = torch.empty((world * B, FRAMES, NFEATS), device=dev) if world > 1 else None   # every rank's [B, 196, 263] slot
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
     eng = model._bind()
 
@@ -218,7 +302,7 @@ def run_own(args):
         feats = model.vae.decode(z, lengths)
         n2 = eng.last_launch_count
         if world > 1:
-            dist.all_gather(gather, feats)                    # the only collective: motions over NVLink
+            dist.all_gather_into_tensor(gather, feats)        # the only collective: motions over NVLink
         return feats, n1 + n2
 
     def step_e2e():
@@ -227,9 +311,11 @@ def run_own(args):
         z = model._diffusion_reverse(t, lengths, latents=nz)
         feats = model.vae.decode(z, lengths)
         if world > 1:
-            dist.all_gather(gather, feats)
+            dist.all_gather_into_tensor(gather, feats)
         out_h.copy_(feats, non_blocking=True)
         return feats
+
+    step_ms = []           # per-batch device times of the last timed() call (sorted)
 
     def timed(fn, K, W):
         for _ in range(W):
@@ -250,8 +336,9 @@ def run_own(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        per = sorted(a.elapsed_time(b) for a, b in evs)
+        step_ms[:] = per
+        t = torch.tensor([sum(per)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
@@ -269,7 +356,9 @@ def run_own(args):
     def run_pipe(n, host):
         for feats in model.sample_stream(batches(n, host)):
             if world > 1:
-                dist.all_gather(gather, feats)                # the only collective: motions over NVLink
+                # the only collective: motions over NVLink, straight into the preallocated [world * B, 196, 263] buffer; it is
+                # enqueued on the caller's stream while the NEXT batch's reverse loop already runs on the high-priority stream
+                dist.all_gather_into_tensor(gather, feats)
             if host:
                 out_h.copy_(feats, non_blocking=True)
 
@@ -299,6 +388,7 @@ def run_own(args):
     if rank == 0:
         sampler.start()
     ms_seq = timed(lambda: step_resident(), args.steps, W)    # one batch at a time (latency view)
+    lat_sorted = list(step_ms)
     ms_total = timed_pipe(args.steps, W, False) if pipelined else ms_seq
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed_pipe(args.steps, W, True) if pipelined else timed(step_e2e, args.steps, W)
@@ -385,34 +475,67 @@ def run_own(args):
         model.text_encoder(texts); torch.cuda.synchronize()
         t0 = time.perf_counter(); model.text_encoder(texts); torch.cuda.synchronize()
         extra["clip_ms"] = (time.perf_counter() - t0) * 1e3
-        # CPU baseline: the reference path (oracle port) on this box's host cores, bounded sample
+        # BASELINE config 4: KIT-ML (251-d features, 196 frames), batch 256, bf16 path (2560 latent rows > 1776: the reverse loop runs the separate fused linears, not k_ffn_swap)
+        kcfg = L.default_config("kit", num_inference_timesteps=STEPS_DDIM)
+        torch.manual_seed(1234)
+        kit = LADIFF(kcfg, SyntheticDataModule(251, 21)).to(dev).eval()
+        kit.text_encoder = None
+        Bk = 256
+        tk = torch.randn((2 * Bk, 1, 768), generator=g).to(dev)
+        nk = torch.randn((Bk, 5, 256), generator=g).to(dev)
+        lk = [FRAMES] * Bk
+        for m in ("bf16", "bf16x3"):
+            kit.set_precision(m)
+            ms_k2 = t_ms(lambda: kit.vae.decode(kit._diffusion_reverse(tk, lk, latents=nk), lk), 3)
+            extra[f"kit256_{m}"] = {"value": Bk / (ms_k2 / 1e3), "unit": "seq/s", "ms": ms_k2,
+                                    "config": "KIT-ML 251-d features, 196 frames, batch 256, 50-step DDIM + CFG 7.5 + decode"}
+        del kit
+        # CPU baseline: the reference path (oracle port) on this box's host cores, on THIS model's weights and THIS step's inputs --
+        # one complete batch (all 50 CFG steps + decode, nothing extrapolated); its output doubles as the live parity check of
+        # the headline configuration in both tensor-core modes
         from oracle import ladiff_oracle as O
         try:
             torch.set_num_threads(len(os.sched_getaffinity(0)))     # all host threads, whatever OMP_NUM_THREADS the launcher exported
         except Exception:
             pass
-        sd = O.make_state_dict(1234, NFEATS, perturb=False)
-        ctext, cnoise, clen = O.synthetic_inputs(B, seed=1234, ragged=False, fixed_len=FRAMES)
-        cpu_reference_step(O, sd, ctext, cnoise, clen, 1)
-        sec, _, _ = cpu_reference_step(O, sd, ctext, cnoise, clen, 5)
+        sd = {"denoiser." + k: v.detach().float().cpu() for k, v in model.denoiser.state_dict().items()}
+        sd.update({"vae." + k: v.detach().float().cpu() for k, v in model.vae.state_dict().items()})
+        cpu_reference_run(O, sd, text_h, noise_h, lengths, 2)
+        sec, ref_feats = cpu_reference_run(O, sd, text_h, noise_h, lengths)
         cpu = {"value": B / sec, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"B={B} L={FRAMES}: 5 of 50 CFG denoiser steps timed and scaled x10 + one full decode, fp32 torch CPU (oracle/ladiff_oracle.py)"}
+               "sample": f"B={B} L={FRAMES}: one complete batch, all {STEPS_DDIM} CFG denoiser steps + DDIM + decode, fp32 torch CPU (oracle/ladiff_oracle.py)"}
+        parity = {"ref_abs_max": float(ref_feats.abs().max()), "against": "cpu_baseline output on the same weights / inputs (oracle as checker)"}
+        for m in ("bf16x3", "bf16"):
+            model.set_precision(m)
+            f = model.vae.decode(model._diffusion_reverse(text_d, lengths, latents=noise_d), lengths).cpu()
+            parity[f"{m}_max_abs_err"] = float((f - ref_feats).abs().max())
+        model.set_precision(args.mode)
+        extra["parity"] = parity
+        # BASELINE config 1: batch 1, 196 frames, 50 steps on the CPU (reference path), and the same on the GPU
+        t1, n1_, l1 = text_h[[0, B]], noise_h[:1], [FRAMES]
+        cpu_reference_run(O, sd, t1, n1_, l1, 2)
+        sec1, _ = cpu_reference_run(O, sd, t1, n1_, l1)
+        ms_g1 = t_ms(lambda: model.vae.decode(model._diffusion_reverse(t1.to(dev), l1, latents=n1_.to(dev)), l1), 5)
+        extra["batch1"] = {"cpu_latency_ms": sec1 * 1e3, "cpu_seq_s": 1.0 / sec1, "cores": torch.get_num_threads(),
+                           "gpu_latency_ms": ms_g1, "gpu_seq_s": 1e3 / ms_g1,
+                           "config": "batch 1, 196 frames, 50-step DDIM + CFG 7.5 + decode (BASELINE config 1)"}
     else:
         cpu = None
 
     out = {
-        "metric": "motion sequences/sec (50-step DDIM+CFG, 196 frames)", "value": value, "unit": "seq/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world,
         "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16 hi/lo split x3 products, fp32 accumulate (fp32-grade, parity 1e-3)", "bf16": "bf16, fp32 accumulate",
+        "dtype": {"bf16x3": "f16 hi/lo split x3 products, fp32 accumulate (fp32-grade, parity 1e-3)", "bf16": "bf16, fp32 accumulate",
                   "fp32": "f32"}[args.mode],
         "data": "synthetic",
-        "config": {"workload": f"LA-DDPM sampling batch {B} per GPU, {STEPS_DDIM}-step DDIM + CFG {GUIDANCE}, {FRAMES} frames, + LA-VAE decode to {NFEATS}-d features",
-                   "weights": "random-init (reference initialiser families), seed 1234", "mode": args.mode,
-                   "l2": "L2 flushed (256 MiB write) between timed iterations", "collective": "all_gather of motions per step" if world > 1 else "none",
-                   "schedule": ("pipelined over the K steps (LADIFF.sample_stream: decode of batch i on a low-priority stream under the reverse "
-                                "loop of batch i+1)") if pipelined else "one batch at a time"},
-        "latency_ms_per_batch": ms_seq / args.steps, "value_sequential": world * B * args.steps / (ms_seq / 1e3),
+        "config": workload_config(B),
+        "run": {"mode": args.mode, "l2": "L2 flushed (256 MiB write) between timed iterations",
+                "collective": "all_gather_into_tensor of motions per step" if world > 1 else "none",
+                "schedule": ("pipelined over the K steps (LADIFF.sample_stream: decode of batch i on a low-priority stream under the reverse "
+                             "loop of batch i+1)") if pipelined else "one batch at a time"},
+        "latency_ms_per_batch": ms_seq / args.steps,
+        "p50_latency_ms": lat_sorted[len(lat_sorted) // 2], "p90_latency_ms": lat_sorted[min(len(lat_sorted) - 1, int(0.9 * len(lat_sorted)))], "value_sequential": world * B * args.steps / (ms_seq / 1e3),
         "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": int(text_h.numel() * 4 + noise_h.numel() * 4),
                 "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches * args.steps),
@@ -453,10 +576,14 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-pipeline", action="store_true", help="time one batch at a time instead of LADIFF.sample_stream")
     ap.add_argument("--quick", action="store_true", help="skip the extra measurements (kernel table, other modes, CPU baseline)")
+    ap.add_argument("--sweep", type=int, default=0, help="BASELINE config 5: this many prompts sharded over the ranks (strong scaling)")
+    ap.add_argument("--micro", type=int, default=B_PER_GPU, help="micro-batch (prompts per call) of the sweep")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.sweep > 0:
+        run_sweep(args)
     else:
         run_own(args)
 

@@ -135,6 +135,17 @@ LADIFF_API int ladiff_cfg_ddim_step(ladiff_handle* h, const float* noise_pred_de
 LADIFF_API int ladiff_vae_decode(ladiff_handle* h, const float* z_dev, const int32_t* lengths_host, int32_t B,
                       int32_t max_len, int32_t mode, float* out_dev, void* stream);
 
+/* LADiffVae.encode(features, lengths) (models/architectures/ladiff_vae.py:162-286; LAD branch, JOINT_DISTRO_FIX false,
+ * MLP_DIST false) -- used by the evaluation glue (ladiff.py:1149 t2m_eval, stage 'vae'), "next" row of the scope table.
+ *   feats_dev [B,max_len,nfeats], lengths_host [B]; token sequence per motion = m mu tokens | m logvar tokens | L frames
+ *   through the non-MD SkipTransformerEncoder (operator/cross_attention.py:48-67), ragged like the decoder.
+ *   eps_dev [T,B,256]: the standard-normal draw of dist.rsample() (NULL -> latent = mu)
+ *   outputs (each optional, [T,B,256]): latent = mu + std*eps with rows t >= m_i exactly zero (:265-268),
+ *   mu = dist.loc, std = dist.scale = exp(logvar)^0.5 for the valid rows (0 / 1 elsewhere). */
+LADIFF_API int ladiff_vae_encode(ladiff_handle* h, const float* feats_dev, const int32_t* lengths_host, int32_t B,
+                      int32_t max_len, const float* eps_dev, int32_t mode, float* latent_dev, float* mu_dev,
+                      float* std_dev, void* stream);
+
 /* datamodule.feats2joints (data/HumanML3D.py:44-48 -> recover_from_ric,
  * data/humanml/scripts/motion_process.py:355-381,415-430), which the reference runs on the CPU
  * after a .cpu() (ladiff.py:307).  feats_dev [B,max_len,nfeats] -> joints_dev [B,max_len,njoints,3]. */
@@ -154,11 +165,11 @@ LADIFF_API int ladiff_linear_test(ladiff_handle* h, const float* A_dev, const fl
 LADIFF_API int ladiff_linear_bench(ladiff_handle* h, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t mode,
                         int32_t iters, float* ms_per_launch_host, void* stream);
 
-/* Test / measurement hook for the cluster-fused feed-forward kernels (csrc/ffn_swap.cuh, csrc/ffn_cluster.cuh): runs the two
- * feed-forward pairs of denoiser layer `layer` (reference: mdiff_transformer.py:60-62 sa_block FFN + norm2, :248-262 FFN +
- * StylizationBlock prologue) on M rows x_dev[M,256] with the finalised denoiser weights; mod_dev = [scale(256) | shift(256)].
- * fused = 1: the fused kernel the plans pick (token-group kernel k_ffn_swap for M <= 1776, else the 128-row cluster kernel);
- * fused = 2: force the 128-row cluster kernel; fused = 0: the four separate fused linears.  Writes x3 and s ([M,256] fp32).  iters > 0: also returns the average
+/* Test / measurement hook for the cluster-fused feed-forward kernel (csrc/ffn_swap.cuh): runs the two feed-forward pairs of
+ * denoiser layer `layer` (reference: mdiff_transformer.py:60-62 sa_block FFN + norm2, :248-262 FFN + StylizationBlock prologue)
+ * on M rows x_dev[M,256] with the finalised denoiser weights; mod_dev = [scale(256) | shift(256)].
+ * fused != 0: what the plans run -- the token-group kernel k_ffn_swap for M <= 1776, the four separate fused linears above;
+ * fused = 0: always the four separate fused linears.  Writes x3 and s ([M,256] fp32).  iters > 0: also returns the average
  * milliseconds of `iters` back-to-back calls (CUDA events on `stream`). */
 LADIFF_API int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t layer, const float* mod_dev, int32_t mode,
                     int32_t fused, int32_t iters, float* x3_out_dev, float* s_out_dev, float* ms_per_call_host, void* stream);

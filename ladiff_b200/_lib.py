@@ -37,6 +37,11 @@ def load_library() -> C.CDLL:
         raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m ladiff_b200.build` "
                            "(the CUDA extension is mandatory, there is no fallback path)")
     lib = C.CDLL(LIB_PATH)
+    missing = [s for s in EXPORTS if not hasattr(lib, s)]
+    if missing and not os.environ.get("LADIFF_LIB"):      # an A/B build of an older revision (LADIFF_LIB) may lack newer entry points
+        raise RuntimeError(f"{LIB_PATH} does not export {missing}: rebuild with `python -m ladiff_b200.build`")
+    for s in missing:
+        setattr(lib, s, None)
     vp, i32, f32, i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
     pi32, pf32 = C.POINTER(C.c_int32), C.POINTER(C.c_float)
     lib.ladiff_abi_version.restype = C.c_int
@@ -53,6 +58,8 @@ def load_library() -> C.CDLL:
     lib.ladiff_denoiser_forward.argtypes = [vp, vp, i32, vp, pi32, i32, i32, vp, vp]
     lib.ladiff_cfg_ddim_step.argtypes = [vp, vp, vp, i32, f32, f32, f32, vp]
     lib.ladiff_vae_decode.argtypes = [vp, vp, pi32, i32, i32, i32, vp, vp]
+    if lib.ladiff_vae_encode is not None:
+        lib.ladiff_vae_encode.argtypes = [vp, vp, pi32, i32, i32, vp, i32, vp, vp, vp, vp]
     lib.ladiff_feats2joints.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.ladiff_linear_test.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.ladiff_linear_bench.argtypes = [vp, i32, i32, i32, i32, i32, i32, pf32, vp]
@@ -62,16 +69,17 @@ def load_library() -> C.CDLL:
     lib.ladiff_last_launch_count.argtypes = [vp]
     lib.ladiff_last_launch_count.restype = i64
     for fn in ("ladiff_create", "ladiff_set_weight", "ladiff_finalize_weights", "ladiff_diffusion_reverse",
-               "ladiff_diffusion_reverse_ex", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step", "ladiff_vae_decode", "ladiff_feats2joints",
+               "ladiff_diffusion_reverse_ex", "ladiff_vae_encode", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step", "ladiff_vae_decode", "ladiff_feats2joints",
                "ladiff_linear_test", "ladiff_linear_bench"):
-        getattr(lib, fn).restype = C.c_int
+        if getattr(lib, fn) is not None:
+            getattr(lib, fn).restype = C.c_int
     _lib = lib
     return lib
 
 
 EXPORTS = ("ladiff_abi_version", "ladiff_create", "ladiff_destroy", "ladiff_last_error", "ladiff_set_weight",
            "ladiff_finalize_weights", "ladiff_diffusion_reverse", "ladiff_diffusion_reverse_ex", "ladiff_denoiser_forward", "ladiff_cfg_ddim_step",
-           "ladiff_vae_decode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_ffn_test", "ladiff_trace_read",
+           "ladiff_vae_decode", "ladiff_vae_encode", "ladiff_feats2joints", "ladiff_linear_test", "ladiff_linear_bench", "ladiff_ffn_test", "ladiff_trace_read",
            "ladiff_last_launch_count")
 
 
@@ -217,6 +225,20 @@ class Engine:
                     "vae_decode")
         return out
 
+    def vae_encode(self, feats: torch.Tensor, lengths: Sequence[int], mode: int, eps: Optional[torch.Tensor] = None):
+        """(latent, mu, std), each [T, B, 256] (ladiff_vae_encode)."""
+        f = _dev32(feats, "features")
+        B, max_len, nf = f.shape
+        if nf != self.nfeats or len(lengths) != B:
+            raise ValueError(f"features must be [{len(lengths)}, max_len, {self.nfeats}], got {tuple(f.shape)}")
+        eps = None if eps is None else _dev32(eps, "eps")
+        if eps is not None and tuple(eps.shape) != (self.max_it, B, 256):
+            raise ValueError(f"eps must be [{self.max_it},{B},256], got {tuple(eps.shape)}")
+        lat, mu, std = (torch.empty((self.max_it, B, 256), device=self.device, dtype=torch.float32) for _ in range(3))
+        self._check(self.lib.ladiff_vae_encode(self._h, _ptr(f), _i32(lengths), B, max_len, _ptr(eps), mode, _ptr(lat), _ptr(mu),
+                                               _ptr(std), _stream()), "vae_encode")
+        return lat, mu, std
+
     def feats2joints(self, feats: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, njoints: int) -> torch.Tensor:
         f = _dev32(feats, "features")
         B, L, _ = f.shape
@@ -252,8 +274,8 @@ class Engine:
 
     def ffn_test(self, x: torch.Tensor, layer: int, mod: torch.Tensor, mode: int = MODE_BF16X3, fused=True, iters: int = 0):
         """(x3, s, ms) of the two feed-forward pairs of denoiser layer `layer` on rows x[M,256] (ladiff_ffn_test).
-        fused: False = four separate fused linears, True = the fused kernel the plans would pick (token-group kernel
-        k_ffn_swap for M <= 1776, else the 128-row cluster kernel), 2 = force the 128-row cluster kernel."""
+        fused: False = four separate fused linears, True = what the plans run (token-group kernel k_ffn_swap for
+        M <= 1776, the separate linears above)."""
         x = x.contiguous().float()
         mod = mod.contiguous().float()
         x3, s = torch.empty_like(x), torch.empty_like(x)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #define LD_D 256      // latent / model width
@@ -9,11 +10,20 @@
 #define LD_HD 64      // head dim
 #define LD_EPS 1e-5f  // LayerNorm eps (torch default; nn.LayerNorm at cross_attention.py:277, mdiff_transformer.py:145)
 
-// An activation tensor [rows, ld]: fp32 master and/or bf16 operand planes for the tensor-core GEMMs.
+// 16-bit tensor-core operand element.  The FORMAT follows the arithmetic mode, i.e. the number of planes a tensor carries:
+//   two planes (mode "x3")  : fp16 hi / lo split, v ~= hi + lo to 22 mantissa bits; the three products a_lo w_hi + a_hi w_lo +
+//                             a_hi w_hi of the GEMMs then carry ~2^-21 relative error (fp32-grade: the 50-step CFG loop amplifies
+//                             operand rounding ~100x, a bf16 hi/lo split (16 bits) measured 1.2e-3 on the B = 128 headline config
+//                             against the 1e-3 contract, profiles/r02a).  Range: |v| < 65504 (activations here are LayerNorm'd
+//                             streams and O(100) latents; weights O(0.1)); values below 2^-14 use fp16 subnormals (abs error 3e-8).
+//   one plane (mode "bf16") : bf16, round to nearest.
+typedef uint16_t op16;
+
+// An activation tensor [rows, ld]: fp32 master and/or 16-bit operand planes for the tensor-core GEMMs.
 // Planes are stacked: hi plane rows [0, rows_alloc), lo plane rows [rows_alloc, 2*rows_alloc); value ~= hi + lo.
 struct Act {
   float* f32;           // may be null
-  __nv_bfloat16* pl;    // may be null
+  op16* pl;             // may be null
   int ld;
   int rows_alloc;       // multiple of 128 so a 128-row TMA box never straddles the planes
 };
@@ -62,28 +72,57 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// hi/lo bf16 split of an fp32 value (lo = bf16(v - float(hi))): v ~= hi + lo to ~16 mantissa bits.
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-
-// Packed variant for two neighbouring columns (x in the low half): F2FP.BF16.F32.PACK_AB runs on the full-rate pipes,
-// the scalar F2F.BF16.F32 conversion does not.  Same round-to-nearest-even results as split_bf16.
-__device__ __forceinline__ void split2_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+// ---- operand splits -----------------------------------------------------------------------------------------------
+// fp16 hi/lo split of two neighbouring columns (x in the low half): F2FP.F16.F32.PACK_AB runs on the full-rate pipes.
+__device__ __forceinline__ void split2_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float xf = __uint_as_float(hi << 16), yf = __uint_as_float(hi & 0xffff0000u);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(x - xf, y - yf);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// bf16 round of two neighbouring columns
+__device__ __forceinline__ uint32_t pack2_bf16_rn(float x, float y) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// bf16 hi/lo split (decoder / encoder self-attention keeps its mma.sync bf16 fragments: its error is 5e-5 on the features)
+__device__ __forceinline__ void split2_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack2_bf16_rn(x, y);
+  const float xf = __uint_as_float(hi << 16), yf = __uint_as_float(hi & 0xffff0000u);
+  lo = pack2_bf16_rn(x - xf, y - yf);
+}
+// the operand format of a tensor with NPL planes (see op16): NPL == 2 -> fp16 hi / lo, else bf16 (lo unused)
+template <int NPL>
+__device__ __forceinline__ void split2_op(float x, float y, uint32_t& hi, uint32_t& lo) {
+  if (NPL == 2) {
+    split2_f16(x, y, hi, lo);
+  } else {
+    hi = pack2_bf16_rn(x, y);
+    lo = 0u;
+  }
+}
+__device__ __forceinline__ void split2_op(float x, float y, int nplanes, uint32_t& hi, uint32_t& lo) {
+  if (nplanes > 1) split2_op<2>(x, y, hi, lo);
+  else split2_op<1>(x, y, hi, lo);
+}
+__device__ __forceinline__ void split_op(float v, int nplanes, op16& hi, op16& lo) {
+  if (nplanes > 1) {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+  } else {
+    hi = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    lo = 0;
+  }
+}
 
-// nplanes: 0 none, 1 hi only, 2 hi + lo
+// nplanes: 0 none, 1 bf16, 2 fp16 hi + lo
 __device__ __forceinline__ void act_store(const Act& a, int nplanes, long row, int col, float v) {
   if (a.f32) a.f32[row * a.ld + col] = v;
   if (a.pl && nplanes > 0) {
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
+    op16 hi, lo;
+    split_op(v, nplanes, hi, lo);
     a.pl[row * a.ld + col] = hi;
     if (nplanes > 1) a.pl[(static_cast<long>(a.rows_alloc) + row) * a.ld + col] = lo;
   }

@@ -1,9 +1,10 @@
-// Fused feed-forward pairs of the denoiser layer, "swapped" formulation for the latency-bound batch sizes (R <= 1776 rows):
+// Fused feed-forward pairs of the denoiser layer, "swapped" formulation for the latency-bound batch sizes (R <= 1776 rows;
+// above that the four separate fused linears are faster -- measured, profiles/r02d_large_batch.txt -- and are what the plans use):
 // the WEIGHT rows sit on the 128 lanes of the tcgen05 M axis and a small group of RT <= 48 tokens on the N axis
 //       h^T  [256-slice x RT]  = W1[slice, :]   . X^T          (phase A, two 128-row M tiles)
 //       out^T[256       x RT]  = W2[:, slice]   . h[:, slice]^T (phase B, K-split partial)
-// so a cluster of only CL = 4 CTAs owns RT tokens (not 128 rows as in ffn_cluster.cuh) and 1280 rows spread over 27 clusters /
-// 108 SMs.  What bounds the fused FFN on B200 is the distributed-shared-memory exchange (~16 B/clk per SM measured,
+// so a cluster of only CL = 4 CTAs owns RT tokens (not a 128-row GEMM tile) and 1280 rows spread over 27 clusters /
+// 108 SMs (an earlier variant with 128-row tiles on clusters of 8 CTAs took 39 us per layer against 24 us).  What bounds the fused FFN on B200 is the distributed-shared-memory exchange (~16 B/clk per SM measured,
 // scripts/micro/dsmem_probe.cu): its volume is  tokens x 1 KB  per CTA whatever the cluster size, so the token group is made
 // small (48 KB per exchange instead of 128 KB) and paid for with weight re-streaming from L2 (512 KB per pair and CTA through a
 // 4-stage TMA ring that runs ahead across the exchanges), which the 126 MB L2 serves at > 80 B/clk per SM.
@@ -19,10 +20,48 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "ffn_cluster.cuh"
 #include "kernels.cuh"
 #include "linear.cuh"
 #include "tc_ptx.cuh"
+
+struct FfnArgs {
+  int M_max;
+  const int* M_dev;
+  int npairs;            // 1 or 2
+  int act[2];            // EPI_RELU / EPI_GELU of the hidden layer
+  int kind[2];           // EPI_LN (+res, +addv) or EPI_LN_MOD_SILU
+  const float* b1[2];    // [1024]
+  const float* b2[2];    // [256]
+  const float* ln_g[2];
+  const float* ln_b[2];
+  const float* res;      // pair 0 residual (fp32 rows of X), ld 256; may be null
+  const float* addv;     // EPI_LN: optional broadcast add
+  const int* add_idx;
+  int ld_add;
+  const float* mod[2];   // EPI_LN_MOD_SILU: [scale(256) | shift(256)]
+  Act out[2];
+  int out_planes;
+  int x_plane_rows;      // row offset of the lo plane in the X tensor map
+  int rt;                // k_ffn_swap: tokens per cluster (16 / 32 / 48)
+  // k_ffn_swap with the sa_block attention fused in front (rt == 48 only): instead of loading X by TMA, every CTA computes
+  //   x1[row] = LN( Xin[row] + b_o + sum_h sum_j softmax_j(q_h . k_hj / 8) v'_hj )   (see k_attn_ln in kernels.cuh)
+  // for its 12 owned rows from the extended in-projection buffer and broadcasts it as the X operand of the cluster
+  int att;                         // 1: fused attention prologue
+  const float* att_qkvx;           // [rows, 1792]: q | k | 4 x v' | X
+  const int* att_off;              // [S + 1] row offsets of the sequences
+  const int* att_row_seq;          // [rows] sequence of a row
+  const float* att_textkv;         // per-sequence conditioning row: k | 4 x v'
+  int att_ld_textkv;
+  const float* att_timekv;         // this (step, layer)'s time-token row: k | 4 x v'
+  const float* att_res;            // layer input rows (residual), ld att_ld_res
+  int att_ld_res;
+  const float *att_bo, *att_g, *att_b;   // out_proj bias, norm1 weight / bias
+  Act att_x1;                      // fp32 master of x1 (residual of pair 0)
+  Act att_xcopy;                   // optional copy of the layer input (U-Net skip source), fp32 and/or planes
+  int w1_plane_rows[2], w2_plane_rows[2];
+  unsigned long long* trace;
+  long long* dbg;        // optional per-CTA clock64 stamps [ncta][128] (ladiff_ffn_test with LADIFF_DBG_STAMPS=1)
+};
 
 template <int NSPLIT>
 struct SwapCfg {
@@ -66,6 +105,11 @@ __device__ __forceinline__ void cluster_sync_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void st_cluster_v2u(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// generic-proxy writes (st.shared / st.shared::cluster) -> visible to the async proxy (tcgen05.mma operand reads), all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void st_cluster_v4u(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -227,15 +271,15 @@ __device__ __forceinline__ void swap_attention_prologue(const FfnArgs& p, uint8_
     const float y0 = valid ? (acc[u].x - mean[u]) * rstd * gc.x + bc.x : 0.f;
     const float y1 = valid ? (acc[u].y - mean[u]) * rstd * gc.y + bc.y : 0.f;
     uint32_t hi, lo;
-    split2_bf16(y0, y1, hi, lo);
+    split2_op<NSPLIT>(y0, y1, hi, lo);
     if (valid) {
       const long row = R0 + i;
       *reinterpret_cast<float2*>(p.att_x1.f32 + row * p.att_x1.ld + c) = make_float2(y0, y1);
       if (p.att_xcopy.f32) *reinterpret_cast<float2*>(p.att_xcopy.f32 + row * p.att_xcopy.ld + c) = xr[u];
       if (p.att_xcopy.pl && p.out_planes > 0) {
         uint32_t xh, xl;
-        split2_bf16(xr[u].x, xr[u].y, xh, xl);
-        __nv_bfloat16* dh = p.att_xcopy.pl + row * p.att_xcopy.ld + c;
+        split2_op(xr[u].x, xr[u].y, p.out_planes, xh, xl);
+        op16* dh = p.att_xcopy.pl + row * p.att_xcopy.ld + c;
         *reinterpret_cast<uint32_t*>(dh) = xh;
         if (p.out_planes > 1) *reinterpret_cast<uint32_t*>(dh + static_cast<long>(p.att_xcopy.rows_alloc) * p.att_xcopy.ld) = xl;
       }
@@ -312,7 +356,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
     tc::mbar_expect_tx(&full[slot], STG);
 #pragma unroll
-    for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(ring + slot * STG + pl * U, m, &full[slot], kcol, pl * prow + row);
+    for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(ring + slot * STG + pl * U, m, &full[slot], kcol, w_plane<NSPLIT>(pl) * prow + row);
   };
 
   if (warp == 0) {
@@ -383,7 +427,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
-    const uint32_t idesc = tc::idesc_bf16_f32(128, rt);
+    const uint32_t idesc = tc::idesc_op<NSPLIT>(128, rt);
     const uint32_t ring_u = tc::smem_u32(ring), xop_u = tc::smem_u32(xop), hr_u = tc::smem_u32(hr);
     const uint32_t tmem_u = tmem_base;
     if (ATT) {
@@ -515,11 +559,11 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             for (int k = 0; k < 8; ++k) {
               float x = v[k] + b1;
               x = relu ? fmaxf(x, 0.f) : gelu_erf_fast(x);
-              __nv_bfloat16 hi, lo;
-              split_bf16(x, hi, lo);
+              op16 hi, lo;
+              split_op(x, NSPLIT, hi, lo);
               const int off = k * 128 + ((chunk ^ k) << 4);
-              *reinterpret_cast<__nv_bfloat16*>(hrow + off) = hi;
-              if (NSPLIT == 2) *reinterpret_cast<__nv_bfloat16*>(hrow + XT + off) = lo;
+              *reinterpret_cast<op16*>(hrow + off) = hi;
+              if (NSPLIT == 2) *reinterpret_cast<op16*>(hrow + XT + off) = lo;
             }
           }
           tc::fence_proxy_async();
@@ -632,8 +676,8 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         uint2 hi2[4], lo2[4];   // per k-block j: features c0 + 64 j .. + 3
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          split2_bf16(y[4 * j], y[4 * j + 1], hi2[j].x, lo2[j].x);
-          split2_bf16(y[4 * j + 2], y[4 * j + 3], hi2[j].y, lo2[j].y);
+          split2_op<NSPLIT>(y[4 * j], y[4 * j + 1], hi2[j].x, lo2[j].x);
+          split2_op<NSPLIT>(y[4 * j + 2], y[4 * j + 3], hi2[j].y, lo2[j].y);
         }
         // the exchange first: it is on the critical path of the next pair, the global stores are not
         if (!last && own) {
@@ -659,7 +703,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           for (int j = 0; j < 4; ++j) {
             if (o.f32) *reinterpret_cast<float4*>(o.f32 + orow * o.ld + c0 + 64 * j) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
             if (o.pl && p.out_planes > 0) {
-              __nv_bfloat16* dh = o.pl + orow * o.ld + c0 + 64 * j;
+              op16* dh = o.pl + orow * o.ld + c0 + 64 * j;
               *reinterpret_cast<uint2*>(dh) = hi2[j];
               if (p.out_planes > 1) *reinterpret_cast<uint2*>(dh + static_cast<long>(o.rows_alloc) * o.ld) = lo2[j];
             }

@@ -221,7 +221,10 @@ __device__ __forceinline__ unsigned long long ktimer() {
 #define DC_LD 1280    // conditioning-token table row per layer: k | 4 x v'
 // SEQS sequences per CTA (256 threads each, independent named barriers): SEQS = 2 halves the grid to <= 148 CTAs at B = 128
 template <int MAXT, int SEQS>
-__global__ void __launch_bounds__(256 * SEQS) k_attn_ln(const float* __restrict__ qkvx, const int* __restrict__ off, int S,
+// min 2 CTAs per SM = at most 128 registers: what matters is the CAP it implies -- never 3 CTAs on one SM.  The kernel starts under
+// the tail of the in-projection (PDL), whose CTAs still hold most SMs; with 3 allowed the few free SMs take 3 CTAs each and become
+// the critical path of this latency-bound link (same-box A/B, profiles/r02_attn_ln_occupancy.txt: reverse loop 20.98 -> 20.52 ms).
+__global__ void __launch_bounds__(256 * SEQS, SEQS == 1 ? 2 : 1) k_attn_ln(const float* __restrict__ qkvx, const int* __restrict__ off, int S,
                                                  const float* __restrict__ textkv, int ld_textkv,
                                                  const float* __restrict__ timekv, const float* __restrict__ res, int ld_res,
                                                  const float* __restrict__ bo, const float* __restrict__ g,
@@ -515,6 +518,64 @@ __global__ void k_z_out(const float* __restrict__ lat, const int* __restrict__ c
   const int t = bt % T, b = bt / T;
   const int m = cnt[b];
   z[(static_cast<long>(t) * B + b) * 256 + c] = (t < m) ? lat[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LA-VAE encoder (LADiffVae.encode, architectures/ladiff_vae.py:162-286): ragged token sequence per motion =
+// [ m mu tokens | m logvar tokens | L frames ]  (the masked distribution tokens / padded frames of the reference never
+// influence a valid row, so they are simply not computed; positions keep the reference's padded layout: mu i at i,
+// logvar i at T + i, frame f at 2 T + f).
+
+// features [B, max_len, nfeats] -> packed frame rows [sum L, Kp] (zero-padded columns), fp32 + bf16 planes
+__global__ void k_enc_pack_feats(const float* __restrict__ feats, int max_len, int nfeats, int Kp, const int* __restrict__ frow_seq,
+                                 const int* __restrict__ frow_t, const int* __restrict__ R_dev, Act out, int planes) {
+  pdl_prologue();
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long row = i / Kp;
+  const int col = static_cast<int>(i % Kp);
+  if (row >= *R_dev) return;
+  const float v = col < nfeats ? feats[(static_cast<long>(frow_seq[row]) * max_len + frow_t[row]) * nfeats + col] : 0.f;
+  act_store(out, planes, row, col, v);
+}
+
+// token rows of the encoder input: global_motion_token / embedded frames + learned positions (ladiff_vae.py:189,213,220)
+__global__ void k_enc_init(const float* __restrict__ gmt, const float* __restrict__ emb, const float* __restrict__ pe, int T,
+                           const int* __restrict__ row_seq, const int* __restrict__ row_t, const int* __restrict__ mcnt,
+                           const int* __restrict__ foff, const int* __restrict__ R_dev, Act x, int planes) {
+  pdl_prologue();
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long row = i >> 8;
+  const int col = static_cast<int>(i & 255);
+  if (row >= *R_dev) return;
+  const int s = row_seq[row], j = row_t[row], m = mcnt[s];
+  float v;
+  if (j < m) v = gmt[j * 256 + col] + pe[j * 256 + col];
+  else if (j < 2 * m) v = gmt[(T + j - m) * 256 + col] + pe[(T + j - m) * 256 + col];
+  else v = emb[(static_cast<long>(foff[s]) + (j - 2 * m)) * 256 + col] + pe[(2 * T + j - 2 * m) * 256 + col];
+  act_store(x, planes, row, col, v);
+}
+
+// mu / std / latent [T, B, 256] from the final tokens (ladiff_vae.py:258-268): std = exp(logvar)^0.5, latent = mu + std eps,
+// rows t >= m: latent exactly 0 (and mu = 0, std = 1: the reference leaves values of masked tokens there that nothing reads)
+__global__ void k_enc_out(const float* __restrict__ tok, const int* __restrict__ off, const int* __restrict__ mcnt, int B, int T,
+                          const float* __restrict__ eps, float* __restrict__ latent, float* __restrict__ mu_out,
+                          float* __restrict__ std_out) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(T) * B * 256) return;
+  const int col = static_cast<int>(i & 255);
+  const long tb = i >> 8;
+  const int b = static_cast<int>(tb % B), t = static_cast<int>(tb / B);
+  const int m = mcnt[b];
+  float mu = 0.f, sd = 1.f, z = 0.f;
+  if (t < m) {
+    const long r = off[b] + t;
+    mu = tok[r * 256 + col];
+    sd = sqrtf(expf(tok[(r + m) * 256 + col]));
+    z = mu + sd * (eps ? eps[i] : 0.f);
+  }
+  if (latent) latent[i] = z;
+  if (mu_out) mu_out[i] = mu;
+  if (std_out) std_out[i] = sd;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -864,7 +925,7 @@ __global__ void __launch_bounds__(256, 1) k_attn_self_tc(const float* __restrict
         if (out.f32) *reinterpret_cast<float2*>(out.f32 + base + nd * 8) = make_float2(x, y);
         if (out.pl && planes > 0) {
           uint32_t hi, lo;
-          split_pack2(x, y, hi, lo);
+          split2_op(x, y, planes, hi, lo);     // the OUTPUT planes follow the mode's operand format (common.cuh op16)
           *reinterpret_cast<uint32_t*>(out.pl + base + nd * 8) = hi;
           if (planes > 1) *reinterpret_cast<uint32_t*>(out.pl + static_cast<long>(out.rows_alloc) * out.ld + base + nd * 8) = lo;
         }
@@ -874,9 +935,10 @@ __global__ void __launch_bounds__(256, 1) k_attn_self_tc(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: W [N, K] (row stride ldw) fp32 -> Wt [K][N] fp32 and bf16 planes [2][n_pad][K] (zero padded rows)
+// weight packing: W [N, K] (row stride ldw) fp32 -> Wt [K][N] fp32 and three 16-bit planes [3][n_pad][K] (zero padded rows):
+// fp16 hi | fp16 lo (x3 mode) | bf16 (bf16 mode)
 __global__ void k_pack_weight(const float* __restrict__ W, int ldw, int N, int K, int n_pad, float* __restrict__ Wt,
-                              __nv_bfloat16* __restrict__ pl) {
+                              op16* __restrict__ pl) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long>(n_pad) * K) return;
   const int n = i / K, k = i % K;
@@ -885,10 +947,12 @@ __global__ void k_pack_weight(const float* __restrict__ W, int ldw, int N, int K
     v = W[static_cast<long>(n) * ldw + k];
     Wt[static_cast<long>(k) * N + n] = v;
   }
-  __nv_bfloat16 hi, lo;
-  split_bf16(v, hi, lo);
+  op16 hi, lo, b, unused;
+  split_op(v, 2, hi, lo);
+  split_op(v, 1, b, unused);
   pl[i] = hi;
   pl[static_cast<long>(n_pad) * K + i] = lo;
+  pl[2 * static_cast<long>(n_pad) * K + i] = b;
 }
 
 // Weight folding at load time (finalize): C[n, k2] = sum_k1 A[n, k1] * B[k1, k2]  (fp32 in, fp64 accumulate, fp32 out).

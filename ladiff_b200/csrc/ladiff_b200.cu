@@ -16,7 +16,6 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "linear.cuh"
-#include "ffn_cluster.cuh"
 #include "ffn_swap.cuh"
 
 namespace {
@@ -71,7 +70,7 @@ struct Raw {
 struct Weight {
   int N = 0, K = 0, n_pad = 0;
   float* Wt = nullptr;
-  __nv_bfloat16* pl = nullptr;
+  op16* pl = nullptr;
   float* bias = nullptr;
   CUtensorMap map64, map128, map256;  // TMA boxes of 64 / 128 / 256 weight rows (one load per plane and k-block)
 };
@@ -109,9 +108,15 @@ struct DecLayerW {
   float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
 };
 
+struct EncLayerW {
+  Weight qkv, out, ff1, ff2;
+  float *n1g, *n1b, *n2g, *n2b;
+};
+
 struct DenoisePlan;
 struct ReversePlan;
 struct DecodePlan;
+struct EncodePlan;
 constexpr int MAX_CHAINS = 8;
 
 }  // namespace
@@ -137,6 +142,13 @@ struct ladiff_handle {
   DecLayerW dec[NL];
   Weight dec_skip[4], dec_final, memkv_all;
   float *dec_fg = nullptr, *dec_fb = nullptr, *dec_pe = nullptr;
+  // LA-VAE encoder (packed with the decoder when its keys are present)
+  EncLayerW enc[NL];
+  Weight enc_skip[4], skel;
+  float *enc_fg = nullptr, *enc_fb = nullptr, *enc_pe = nullptr, *enc_gmt = nullptr;
+  int skel_kp = 0;
+  bool enc_ready = false;
+  std::map<std::string, std::unique_ptr<EncodePlan>> enc_plans;
   std::map<std::string, std::unique_ptr<DenoisePlan>> den_plans;
   std::map<std::string, std::unique_ptr<ReversePlan>> rev_plans;
   std::map<std::string, std::unique_ptr<DecodePlan>> dec_plans;
@@ -162,12 +174,12 @@ const char* block_name(int l) {
   return n[l];
 }
 
-int make_map(H* h, CUtensorMap* m, const __nv_bfloat16* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_map(H* h, CUtensorMap* m, const op16* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(__nv_bfloat16)};
+  cuuint64_t strides[1] = {ld * sizeof(op16)};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<op16*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return h->err.set(LADIFF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
@@ -189,8 +201,8 @@ int alloc_act(H* h, Arena& ar, ActBuf* b, int rows, int ld, bool f32, bool plane
     CK(cudaMemset(b->act.f32, 0, n * sizeof(float)));
   }
   if (planes) {
-    CK(ar.alloc(reinterpret_cast<void**>(&b->act.pl), 2 * n * sizeof(__nv_bfloat16)));
-    CK(cudaMemset(b->act.pl, 0, 2 * n * sizeof(__nv_bfloat16)));
+    CK(ar.alloc(reinterpret_cast<void**>(&b->act.pl), 2 * n * sizeof(op16)));
+    CK(cudaMemset(b->act.pl, 0, 2 * n * sizeof(op16)));
     CKS(make_map(h, &b->map, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 128));
     CKS(make_map(h, &b->map16, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 16));
     CKS(make_map(h, &b->map32, b->act.pl, 2ull * b->act.rows_alloc, ld, ld, 32));
@@ -370,7 +382,7 @@ int launch_linear(H* h, cudaStream_t st, int mode, const LinCall& c) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused FFN pairs on a cluster (ffn_cluster.cuh): up to two (W1, act, W2, LayerNorm-kind) pairs chained on one 128-row tile
+// fused FFN pairs on a cluster of 4 CTAs (ffn_swap.cuh): up to two (W1, act, W2, LayerNorm-kind) pairs chained on one token group
 struct FfnPair {
   const Weight* W1 = nullptr;
   const Weight* W2 = nullptr;
@@ -390,7 +402,6 @@ struct FfnCall {
   int ld_add = 256;
   int out_planes = 0;
   long long* dbg = nullptr;
-  bool force_cluster = false;  // tests: the 128-row cluster kernel even where the swapped kernel would be chosen
   // fused sa_block attention prologue (k_ffn_swap, rt == 48): X is computed in the kernel instead of being loaded
   bool att = false;
   const float *att_qkvx = nullptr, *att_textkv = nullptr, *att_timekv = nullptr, *att_res = nullptr;
@@ -400,10 +411,11 @@ struct FfnCall {
   Act att_x1{nullptr, nullptr, 0, 0}, att_xcopy{nullptr, nullptr, 0, 0};
 };
 
-bool ffn_cluster_enabled() { return getenv("LADIFF_NO_FFN_CLUSTER") == nullptr; }
+bool ffn_fused_enabled() { return getenv("LADIFF_NO_FFN_FUSED") == nullptr; }
 
 // Token-group size of the swapped kernel (ffn_swap.cuh): the smallest multiple of 16 whose clusters of 4 CTAs are all
-// co-resident on the 148 SMs; 0 = too many rows, use the 128-row cluster kernel.
+// co-resident on the 148 SMs; 0 = too many rows: the plans then run the four separate fused linears (at >= 2560 rows their
+// 128-row tiles fill the SMs and beat every cluster-fused variant: B = 256 reverse loop 36.8 vs 47.3 ms, B = 1024 107.6 vs 131 ms).
 int ffn_swap_rt(int M_max) {
   if (getenv("LADIFF_NO_FFN_SWAP")) return 0;
   if (const char* e = getenv("LADIFF_FFN_RT")) {
@@ -422,10 +434,10 @@ bool ffn_att_fusable(int M_max, int T) {
   return e && atoi(e) == 1 && T <= 5 && ffn_swap_rt(M_max) == 48;
 }
 
-int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
-  if (mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "ffn cluster kernel is a tensor-core path");
+int launch_ffn_swap(H* h, cudaStream_t st, int mode, const FfnCall& c) {
+  if (mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "the fused feed-forward kernel is a tensor-core path");
   if (c.npairs < 1 || c.npairs > 2 || !c.X || !c.X->has_map || c.X->act.ld != 256)
-    return h->err.set(LADIFF_ERR_INVALID, "ffn cluster: bad operands");
+    return h->err.set(LADIFF_ERR_INVALID, "ffn swap: bad operands");
   if (c.M_max <= 0) return LADIFF_OK;
   FfnArgs a;
   memset(&a, 0, sizeof(a));
@@ -435,8 +447,8 @@ int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
   for (int i = 0; i < c.npairs; ++i) {
     const FfnPair& q = c.pair[i];
     if (!q.W1 || !q.W2 || q.W1->N != 1024 || q.W1->K != 256 || q.W2->N != 256 || q.W2->K != 1024)
-      return h->err.set(LADIFF_ERR_INVALID, "ffn cluster: pair %d must be 256 -> 1024 -> 256", i);
-    if (q.kind != EPI_LN && q.kind != EPI_LN_MOD_SILU) return h->err.set(LADIFF_ERR_INVALID, "ffn cluster: bad epilogue kind");
+      return h->err.set(LADIFF_ERR_INVALID, "ffn swap: pair %d must be 256 -> 1024 -> 256", i);
+    if (q.kind != EPI_LN && q.kind != EPI_LN_MOD_SILU) return h->err.set(LADIFF_ERR_INVALID, "ffn swap: bad epilogue kind");
     a.act[i] = q.act;
     a.kind[i] = q.kind;
     a.b1[i] = q.W1->bias;
@@ -459,42 +471,31 @@ int launch_ffn_cluster(H* h, cudaStream_t st, int mode, const FfnCall& c) {
   if (h->trace && h->trace_n < h->trace_cap) {
     a.trace = h->trace + 8ull * h->trace_n;
     char nm[96];
-    snprintf(nm, sizeof(nm), "ffn_cluster M%d pairs%d", c.M_max, c.npairs);
+    snprintf(nm, sizeof(nm), "ffn_swap M%d pairs%d", c.M_max, c.npairs);
     if (static_cast<int>(h->trace_names.size()) <= h->trace_n) h->trace_names.resize(h->trace_n + 1);
     h->trace_names[h->trace_n] = nm;
     h->trace_n++;
   }
   const FfnPair& q0 = c.pair[0];
   const FfnPair& q1 = c.pair[c.npairs - 1];
-  const int rt = c.force_cluster ? 0 : ffn_swap_rt(c.M_max);
+  const int rt = ffn_swap_rt(c.M_max);
+  if (rt == 0) return h->err.set(LADIFF_ERR_INVALID, "ffn swap: %d rows exceed the co-resident cluster capacity (callers use the separate linears)", c.M_max);
   if (c.att && rt != 48) return h->err.set(LADIFF_ERR_INVALID, "ffn swap: the fused attention prologue needs token groups of 48");
-  if (rt > 0) {
-    a.rt = rt;
-    if (c.att) {
-      a.att = 1;
-      a.att_qkvx = c.att_qkvx; a.att_off = c.att_off; a.att_row_seq = c.att_row_seq; a.att_textkv = c.att_textkv;
-      a.att_ld_textkv = c.att_ld_textkv; a.att_timekv = c.att_timekv; a.att_res = c.att_res; a.att_ld_res = c.att_ld_res;
-      a.att_bo = c.att_bo; a.att_g = c.att_g; a.att_b = c.att_b; a.att_x1 = c.att_x1; a.att_xcopy = c.att_xcopy;
-    }
-    if (a.trace) h->trace_names[h->trace_n - 1] = std::string(c.att ? "attn+ffn_swap M" : "ffn_swap M") + std::to_string(c.M_max) + " rt" + std::to_string(rt);
-    dim3 grid((c.M_max + rt - 1) / rt, 4);
-    const CUtensorMap& mx = rt == 16 ? c.X->map16 : (rt == 32 ? c.X->map32 : c.X->map48);
-    auto kern = mode == LADIFF_MODE_BF16X3 ? (c.att ? k_ffn_swap<2, true> : k_ffn_swap<2, false>)
-                                           : (c.att ? k_ffn_swap<1, true> : k_ffn_swap<1, false>);
-    const int smem = mode == LADIFF_MODE_BF16X3 ? SwapCfg<2>::smem_bytes(rt) : SwapCfg<1>::smem_bytes(rt);
-    CK(launch_pdl(kern, grid, dim3(SwapCfg<2>::THREADS), smem, st, mx, q0.W1->map128, q0.W2->map128, q1.W1->map128,
-                  q1.W2->map128, a));
-    h->launches++;
-    return LADIFF_OK;
+  a.rt = rt;
+  if (c.att) {
+    a.att = 1;
+    a.att_qkvx = c.att_qkvx; a.att_off = c.att_off; a.att_row_seq = c.att_row_seq; a.att_textkv = c.att_textkv;
+    a.att_ld_textkv = c.att_ld_textkv; a.att_timekv = c.att_timekv; a.att_res = c.att_res; a.att_ld_res = c.att_ld_res;
+    a.att_bo = c.att_bo; a.att_g = c.att_g; a.att_b = c.att_b; a.att_x1 = c.att_x1; a.att_xcopy = c.att_xcopy;
   }
-  const int tiles_m = (c.M_max + 127) / 128;
-  dim3 grid(tiles_m, 8);
-  if (mode == LADIFF_MODE_BF16X3)
-    CK(launch_pdl(k_ffn_cluster<2>, grid, dim3(FfnCfg<2>::THREADS), FfnCfg<2>::SMEM_BYTES, st, c.X->map, q0.W1->map128, q0.W2->map256,
-                  q1.W1->map128, q1.W2->map256, a));
-  else
-    CK(launch_pdl(k_ffn_cluster<1>, grid, dim3(FfnCfg<1>::THREADS), FfnCfg<1>::SMEM_BYTES, st, c.X->map, q0.W1->map128, q0.W2->map256,
-                  q1.W1->map128, q1.W2->map256, a));
+  if (a.trace) h->trace_names[h->trace_n - 1] = std::string(c.att ? "attn+ffn_swap M" : "ffn_swap M") + std::to_string(c.M_max) + " rt" + std::to_string(rt);
+  dim3 grid((c.M_max + rt - 1) / rt, 4);
+  const CUtensorMap& mx = rt == 16 ? c.X->map16 : (rt == 32 ? c.X->map32 : c.X->map48);
+  auto kern = mode == LADIFF_MODE_BF16X3 ? (c.att ? k_ffn_swap<2, true> : k_ffn_swap<2, false>)
+                                         : (c.att ? k_ffn_swap<1, true> : k_ffn_swap<1, false>);
+  const int smem = mode == LADIFF_MODE_BF16X3 ? SwapCfg<2>::smem_bytes(rt) : SwapCfg<1>::smem_bytes(rt);
+  CK(launch_pdl(kern, grid, dim3(SwapCfg<2>::THREADS), smem, st, mx, q0.W1->map128, q0.W2->map128, q1.W1->map128,
+                q1.W2->map128, a));
   h->launches++;
   return LADIFF_OK;
 }
@@ -537,7 +538,7 @@ int pack_weight(H* h, Arena& ar, cudaStream_t st, Weight* w, const float* W_dev,
   w->K = K;
   w->n_pad = roundup(N, 256);
   CK(ar.alloc(reinterpret_cast<void**>(&w->Wt), static_cast<size_t>(N) * K * sizeof(float)));
-  CK(ar.alloc(reinterpret_cast<void**>(&w->pl), 2ull * w->n_pad * K * sizeof(__nv_bfloat16)));
+  CK(ar.alloc(reinterpret_cast<void**>(&w->pl), 3ull * w->n_pad * K * sizeof(op16)));   // fp16 hi | fp16 lo | bf16
   w->bias = nullptr;
   if (bias_dev) {
     CK(ar.alloc(reinterpret_cast<void**>(&w->bias), N * sizeof(float)));
@@ -545,9 +546,9 @@ int pack_weight(H* h, Arena& ar, cudaStream_t st, Weight* w, const float* W_dev,
   }
   LAUNCH(k_pack_weight, cdiv(static_cast<long>(w->n_pad) * K, 256), 256, 0, st, W_dev, ldw, N, K, w->n_pad, w->Wt, w->pl);
   if (K % 64 == 0) {
-    CKS(make_map(h, &w->map64, w->pl, 2ull * w->n_pad, K, K, 64));
-    CKS(make_map(h, &w->map128, w->pl, 2ull * w->n_pad, K, K, 128));
-    CKS(make_map(h, &w->map256, w->pl, 2ull * w->n_pad, K, K, 256));
+    CKS(make_map(h, &w->map64, w->pl, 3ull * w->n_pad, K, K, 64));
+    CKS(make_map(h, &w->map128, w->pl, 3ull * w->n_pad, K, K, 128));
+    CKS(make_map(h, &w->map256, w->pl, 3ull * w->n_pad, K, K, 256));
   }
   return LADIFF_OK;
 }
@@ -758,6 +759,46 @@ int finalize_decoder(H* h, cudaStream_t st) {
   CKS(pack_concat(h, st, &h->memkv_all, memproj, D, 2 * D, D));
   CKS(pack_linear(h, st, &h->dec_final, P + "final_layer", h->cfg.nfeats, D));
   h->dec_ready = true;
+  // ---- encoder half of the VAE (LADiffVae.encode; only when the caller supplied its keys)
+  h->enc_ready = false;
+  if (h->raw.count(P + "skel_embedding.weight") && h->raw.count(P + "encoder.norm.weight")) {
+    const int nf = h->cfg.nfeats, Kp = roundup(nf, 64), T = h->cfg.max_it;
+    const Raw *sw, *sb, *gmt, *epe;
+    CKS(get_raw(h, P + "skel_embedding.weight", {D, nf}, &sw));
+    CKS(get_raw(h, P + "skel_embedding.bias", {D}, &sb));
+    CKS(get_raw(h, P + "global_motion_token", {2 * T, D}, &gmt));
+    CKS(get_raw(h, P + "query_pos_encoder.pe", {500, 1, D}, &epe));
+    h->enc_gmt = gmt->dev;
+    h->enc_pe = epe->dev;
+    h->skel_kp = Kp;
+    float* tmp = nullptr;   // [256, Kp] zero-padded copy: the tensor path needs K % 64 == 0
+    CK(cudaMalloc(&tmp, static_cast<size_t>(D) * Kp * sizeof(float)));
+    CK(cudaMemsetAsync(tmp, 0, static_cast<size_t>(D) * Kp * sizeof(float), st));
+    LAUNCH(k_copy2d, cdiv(static_cast<long>(D) * nf, 256), 256, 0, st, sw->dev, nf, D, nf, tmp, Kp);
+    int s_ = pack_weight(h, *h->warena, st, &h->skel, tmp, Kp, D, Kp, sb->dev);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    CKS(s_);
+    CKS(get_vec(h, P + "encoder.norm.weight", D, &h->enc_fg));
+    CKS(get_vec(h, P + "encoder.norm.bias", D, &h->enc_fb));
+    for (int l = 0; l < NL; ++l) {
+      const std::string L = P + "encoder." + block_name(l) + ".";
+      EncLayerW& w = h->enc[l];
+      const Raw *ipw, *ipb;
+      CKS(get_raw(h, L + "self_attn.in_proj_weight", {3 * D, D}, &ipw));
+      CKS(get_raw(h, L + "self_attn.in_proj_bias", {3 * D}, &ipb));
+      CKS(pack_weight(h, *h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
+      CKS(pack_linear(h, st, &w.out, L + "self_attn.out_proj", D, D));
+      CKS(pack_linear(h, st, &w.ff1, L + "linear1", h->cfg.ff_size, D));
+      CKS(pack_linear(h, st, &w.ff2, L + "linear2", D, h->cfg.ff_size));
+      CKS(get_vec(h, L + "norm1.weight", D, &w.n1g));
+      CKS(get_vec(h, L + "norm1.bias", D, &w.n1b));
+      CKS(get_vec(h, L + "norm2.weight", D, &w.n2g));
+      CKS(get_vec(h, L + "norm2.bias", D, &w.n2b));
+    }
+    for (int i = 0; i < 4; ++i) CKS(pack_linear(h, st, &h->enc_skip[i], P + "encoder.linear_blocks." + std::to_string(i), D, 2 * D));
+    h->enc_ready = true;
+  }
   return LADIFF_OK;
 }
 
@@ -938,7 +979,8 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   const int mode = p->mode, pl = p->planes, R = p->Rmax, S = p->S, n = p->n;
   LinCall c;
   unsigned long long* tr = nullptr;
-  const bool fuse_att = mode != LADIFF_MODE_FP32 && ffn_cluster_enabled() && ffn_att_fusable(R, p->T);
+  const bool fused_ffn = mode != LADIFF_MODE_FP32 && ffn_fused_enabled() && ffn_swap_rt(R) > 0;
+  const bool fuse_att = fused_ffn && ffn_att_fusable(R, p->T);
   if (!fuse_att && h->trace && h->trace_n < h->trace_cap) {
     tr = h->trace + 8ull * h->trace_n;
     if (static_cast<int>(h->trace_names.size()) <= h->trace_n) h->trace_names.resize(h->trace_n + 1);
@@ -957,7 +999,7 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   } else
     LAUNCHP((k_attn_ln<8, 1>), S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
-  if (mode != LADIFF_MODE_FP32 && ffn_cluster_enabled()) {
+  if (fused_ffn) {
     // both feed-forward pairs of the layer in ONE cluster kernel: x1 -> x3 (fp32 + planes) -> s (planes); h never leaves the SM
     FfnCall f;
     f.X = &p->x1; f.M_max = R; f.M_dev = p->R; f.npairs = 2; f.out_planes = pl;
@@ -977,7 +1019,7 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
       f.att_bo = w.out_bias; f.att_g = w.n1g; f.att_b = w.n1b;
       f.att_x1 = p->x1.act; f.att_xcopy = xcopy;
     }
-    return launch_ffn_cluster(h, st, mode, f);
+    return launch_ffn_swap(h, st, mode, f);
   }
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
@@ -1171,27 +1213,33 @@ int build_decode_plan(H* h, DecodePlan* p, int B, int mode) {
   return LADIFF_OK;
 }
 
+// ragged self-attention of B sequences of at most Lmax rows (qkv [rows, 768], off[B + 1]) -> out [rows, 256]
+int enqueue_self_attention(H* h, cudaStream_t st, int mode, int pl, int B, int Lmax, const float* qkv, const int* off, const Act& out) {
+  if (mode == LADIFF_MODE_FP32 || getenv("LADIFF_ATTN_SIMT")) {
+    dim3 grid((Lmax + SA_QB - 1) / SA_QB, 4, B);
+    LAUNCHP(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, qkv, off, out, pl);
+  } else {
+    // tensor-core modes: (head, sequence) CTAs, hi/lo split products in bf16x3 mode
+    dim3 grid(4, B);
+    const bool big = Lmax > 26 * 8;
+    if (mode == LADIFF_MODE_BF16X3) {
+      if (big) LAUNCHP((k_attn_self_tc<32, 2>), grid, 256, sat_smem_bytes<32>(2), st, qkv, off, out, pl);
+      else LAUNCHP((k_attn_self_tc<26, 2>), grid, 256, sat_smem_bytes<26>(2), st, qkv, off, out, pl);
+    } else {
+      if (big) LAUNCHP((k_attn_self_tc<32, 1>), grid, 256, sat_smem_bytes<32>(1), st, qkv, off, out, pl);
+      else LAUNCHP((k_attn_self_tc<26, 1>), grid, 256, sat_smem_bytes<26>(1), st, qkv, off, out, pl);
+    }
+  }
+  return LADIFF_OK;
+}
+
 int enqueue_dec_layer(H* h, DecodePlan* p, cudaStream_t st, int l, const ActBuf& in, const ActBuf& out) {
   const DecLayerW& w = h->dec[l];
   const int mode = p->mode, pl = p->planes, R = p->Rmax;
   LinCall c;
   c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->Rf; c.out = f32_only(p->qkv, 768);
   CKS(launch_linear(h, st, mode, c));
-  if (mode == LADIFF_MODE_FP32 || getenv("LADIFF_ATTN_SIMT")) {
-    dim3 grid((p->Lmax + SA_QB - 1) / SA_QB, 4, p->B);
-    LAUNCHP(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, p->qkv, p->foff, p->a.act, pl);
-  } else {
-    // tensor-core modes: (head, sequence) CTAs, hi/lo split products in bf16x3 mode
-    dim3 grid(4, p->B);
-    const bool big = p->Lmax > 26 * 8;
-    if (mode == LADIFF_MODE_BF16X3) {
-      if (big) LAUNCHP((k_attn_self_tc<32, 2>), grid, 256, sat_smem_bytes<32>(2), st, p->qkv, p->foff, p->a.act, pl);
-      else LAUNCHP((k_attn_self_tc<26, 2>), grid, 256, sat_smem_bytes<26>(2), st, p->qkv, p->foff, p->a.act, pl);
-    } else {
-      if (big) LAUNCHP((k_attn_self_tc<32, 1>), grid, 256, sat_smem_bytes<32>(1), st, p->qkv, p->foff, p->a.act, pl);
-      else LAUNCHP((k_attn_self_tc<26, 1>), grid, 256, sat_smem_bytes<26>(1), st, p->qkv, p->foff, p->a.act, pl);
-    }
-  }
+  CKS(enqueue_self_attention(h, st, mode, pl, p->B, p->Lmax, p->qkv, p->foff, p->a.act));
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
@@ -1233,6 +1281,103 @@ int enqueue_decode_body(H* h, DecodePlan* p, cudaStream_t st) {
   }
   LAUNCHP(k_layernorm256, cdiv(static_cast<long>(p->Rmax) * 32, 256), 256, 0, st, p->xa.act.f32, 256, p->Rmax, p->Rf, h->dec_fg, h->dec_fb,
          p->xn.act, pl);
+  return LADIFF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder plan (LADiffVae.encode): token rows = sum_b (2 m_b + L_b)
+struct EncodePlan {
+  Arena ar;
+  int B = 0, mode = 0, T = 0, Lmax = 0, Rmax = 0, Fmax = 0, planes = 0;
+  int *cnt = nullptr, *off = nullptr, *R = nullptr, *row_seq = nullptr, *row_t = nullptr;
+  int *fcnt = nullptr, *foff = nullptr, *Rf = nullptr, *frow_seq = nullptr, *frow_t = nullptr, *mcnt = nullptr;
+  ActBuf feats, x0, xa, xb, x1, skip[4], a, hbuf;
+  float *emb = nullptr, *qkv = nullptr, *xn = nullptr;
+  uint64_t last_use = 0;
+};
+
+int build_encode_plan(H* h, EncodePlan* p, int B, int mode) {
+  p->B = B;
+  p->mode = mode;
+  p->T = h->cfg.max_it;
+  p->Lmax = h->cfg.max_frames + 2 * p->T;
+  p->Fmax = B * h->cfg.max_frames;
+  p->Rmax = B * p->Lmax;
+  p->planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
+  const bool tcm = mode != LADIFF_MODE_FP32, f = !tcm;
+  Arena& ar = p->ar;
+  const int R = p->Rmax, F = p->Fmax;
+  CK(ar.alloc((void**)&p->cnt, B * sizeof(int)));
+  CK(ar.alloc((void**)&p->off, (B + 1) * sizeof(int)));
+  CK(ar.alloc((void**)&p->R, sizeof(int)));
+  CK(ar.alloc((void**)&p->row_seq, R * sizeof(int)));
+  CK(ar.alloc((void**)&p->row_t, R * sizeof(int)));
+  CK(ar.alloc((void**)&p->fcnt, B * sizeof(int)));
+  CK(ar.alloc((void**)&p->foff, (B + 1) * sizeof(int)));
+  CK(ar.alloc((void**)&p->Rf, sizeof(int)));
+  CK(ar.alloc((void**)&p->frow_seq, F * sizeof(int)));
+  CK(ar.alloc((void**)&p->frow_t, F * sizeof(int)));
+  CK(ar.alloc((void**)&p->mcnt, B * sizeof(int)));
+  CKS(alloc_act(h, ar, &p->feats, F, h->skel_kp, f, tcm));
+  CK(ar.alloc((void**)&p->emb, static_cast<size_t>(roundup(F, 128)) * 256 * sizeof(float)));
+  CKS(alloc_act(h, ar, &p->x0, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->xa, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->xb, R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->x1, R, 256, true, tcm));
+  for (int i = 0; i < 4; ++i) CKS(alloc_act(h, ar, &p->skip[i], R, 256, true, tcm));
+  CKS(alloc_act(h, ar, &p->a, R, 256, f, tcm));
+  CKS(alloc_act(h, ar, &p->hbuf, R, 1024, f, tcm));
+  CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * 768 * sizeof(float)));
+  CK(ar.alloc((void**)&p->xn, static_cast<size_t>(roundup(R, 128)) * 256 * sizeof(float)));
+  return LADIFF_OK;
+}
+
+int enqueue_self_attention(H* h, cudaStream_t st, int mode, int planes, int B, int Lmax, const float* qkv, const int* off, const Act& out);
+
+// TransformerEncoderLayer.forward_post (operator/cross_attention.py:293-307, gelu): self-attention -> +res -> LN -> FFN -> +res -> LN
+int enqueue_enc_layer(H* h, EncodePlan* p, cudaStream_t st, int l, const ActBuf& in, const ActBuf& out) {
+  const EncLayerW& w = h->enc[l];
+  const int mode = p->mode, pl = p->planes, R = p->Rmax;
+  LinCall c;
+  c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
+  CKS(launch_linear(h, st, mode, c));
+  CKS(enqueue_self_attention(h, st, mode, pl, p->B, p->Lmax, p->qkv, p->off, p->a.act));
+  c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = in.act.f32;
+  c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_GELU; c.out = p->hbuf.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = p->x1.act.f32;
+  c.ln_g = w.n2g; c.ln_b = w.n2b; c.out = out.act; c.out_planes = pl;
+  CKS(launch_linear(h, st, mode, c));
+  return LADIFF_OK;
+}
+
+// SkipTransformerEncoder.forward, non-MD branch (operator/cross_attention.py:48-67) over the ragged token rows
+int enqueue_encode_body(H* h, EncodePlan* p, cudaStream_t st, const float* feats_dev, int max_len) {
+  const int pl = p->planes, mode = p->mode, Kp = h->skel_kp;
+  LAUNCHP(k_enc_pack_feats, cdiv(static_cast<long>(p->Fmax) * Kp, 256), 256, 0, st, feats_dev, max_len, h->cfg.nfeats, Kp, p->frow_seq,
+          p->frow_t, p->Rf, p->feats.act, pl);
+  LinCall c;
+  c.A = &p->feats; c.W = &h->skel; c.M_max = p->Fmax; c.M_dev = p->Rf; c.out = f32_only(p->emb, 256);
+  CKS(launch_linear(h, st, mode, c));
+  LAUNCHP(k_enc_init, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, h->enc_gmt, p->emb, h->enc_pe, p->T, p->row_seq, p->row_t,
+          p->mcnt, p->foff, p->R, p->x0.act, pl);
+  const ActBuf* x = &p->x0;
+  for (int i = 0; i < 4; ++i) {
+    CKS(enqueue_enc_layer(h, p, st, i, *x, p->skip[i]));
+    x = &p->skip[i];
+  }
+  CKS(enqueue_enc_layer(h, p, st, 4, *x, p->xa));
+  for (int i = 0; i < 4; ++i) {
+    c = LinCall();
+    c.A = &p->xa; c.A2 = &p->skip[3 - i]; c.W = &h->enc_skip[i]; c.M_max = p->Rmax; c.M_dev = p->R;
+    c.out = p->xb.act; c.out_planes = pl;
+    CKS(launch_linear(h, st, mode, c));
+    CKS(enqueue_enc_layer(h, p, st, 5 + i, p->xb, p->xa));
+  }
+  LAUNCHP(k_layernorm256, cdiv(static_cast<long>(p->Rmax) * 32, 256), 256, 0, st, p->xa.act.f32, 256, p->Rmax, p->R, h->enc_fg, h->enc_fb,
+          f32_only(p->xn, 256), 0);
   return LADIFF_OK;
 }
 
@@ -1359,8 +1504,6 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(2));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<32>(1));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(1));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<2>::SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<1>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<1>::smem_bytes(48));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
@@ -1404,6 +1547,7 @@ void ladiff_destroy(ladiff_handle* h) {
   h->den_plans.clear();
   h->rev_plans.clear();
   h->dec_plans.clear();
+  h->enc_plans.clear();
   for (auto& kv : h->raw) cudaFree(kv.second.dev);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int c = 0; c < MAX_CHAINS; ++c) {
@@ -1447,6 +1591,7 @@ int ladiff_finalize_weights(ladiff_handle* h, int32_t which, void* stream) {
   }
   if (which & 2) {
     h->dec_plans.clear();
+    h->enc_plans.clear();
     CKS(finalize_decoder(h, st));
   }
   CK(cudaStreamSynchronize(st));
@@ -1632,6 +1777,51 @@ int ladiff_vae_decode(ladiff_handle* h, const float* z_dev, const int32_t* lengt
   return LADIFF_OK;
 }
 
+int ladiff_vae_encode(ladiff_handle* h, const float* feats_dev, const int32_t* lengths_host, int32_t B, int32_t max_len,
+                      const float* eps_dev, int32_t mode, float* latent_dev, float* mu_dev, float* std_dev, void* stream) {
+  if (!h) return LADIFF_ERR_INVALID;
+  h->launches = 0;
+  if (!h->dec_ready || !h->enc_ready) return h->err.set(LADIFF_ERR_STATE, "vae encoder weights not finalised (vae.encoder.* / vae.skel_embedding.* missing?)");
+  CKS(check_mode(h, mode));
+  if (!feats_dev || !lengths_host || B < 1 || max_len < 1 || (!latent_dev && !mu_dev && !std_dev))
+    return h->err.set(LADIFF_ERR_INVALID, "ladiff_vae_encode: bad argument");
+  const int T = h->cfg.max_it;
+  if (h->cfg.max_frames + 2 * T > SA_MAXL) return h->err.set(LADIFF_ERR_INVALID, "encode: max_frames + 2 max_it must be <= %d", SA_MAXL);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<int> cnt(B), fcnt(B), mcnt(B);
+  for (int b = 0; b < B; ++b) {
+    const int L = lengths_host[b];
+    if (L < 1 || L > h->cfg.max_frames || L > max_len)
+      return h->err.set(LADIFF_ERR_INVALID, "lengths[%d] = %d outside [1, min(max_frames=%d, max_len=%d)]", b, L, h->cfg.max_frames, max_len);
+    int m = (L + h->cfg.frame_per_latent - 1) / h->cfg.frame_per_latent;
+    m = m < T ? m : T;
+    mcnt[b] = m;
+    fcnt[b] = L;
+    cnt[b] = 2 * m + L;
+  }
+  char key[96];
+  snprintf(key, sizeof(key), "enc:%d:%d", B, mode);
+  auto& slot = h->enc_plans[key];
+  if (!slot) {
+    slot.reset(new EncodePlan());
+    int s = build_encode_plan(h, slot.get(), B, mode);
+    if (s != LADIFF_OK) {
+      h->enc_plans.erase(key);
+      return s;
+    }
+    evict_lru(h->enc_plans, key);
+  }
+  EncodePlan* p = h->enc_plans[key].get();
+  p->last_use = ++h->use_clock;
+  CKS(enqueue_meta(h, st, cnt.data(), B, p->cnt, p->off, p->R, p->row_seq, p->row_t, nullptr, 0));
+  CKS(enqueue_meta(h, st, fcnt.data(), B, p->fcnt, p->foff, p->Rf, p->frow_seq, p->frow_t, nullptr, 0));
+  CK(cudaMemcpyAsync(p->mcnt, mcnt.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  g_skip_pdl_once = true;   // first kernel after plain copies
+  CKS(enqueue_encode_body(h, p, st, feats_dev, max_len));
+  LAUNCH(k_enc_out, cdiv(static_cast<long>(T) * B * 256, 256), 256, 0, st, p->xn, p->off, p->mcnt, B, T, eps_dev, latent_dev, mu_dev, std_dev);
+  return LADIFF_OK;
+}
+
 int ladiff_feats2joints(ladiff_handle* h, const float* feats_dev, const float* mean_dev, const float* std_dev, int32_t B,
                         int32_t max_len, int32_t njoints, float* joints_dev, void* stream) {
   if (!h) return LADIFF_ERR_INVALID;
@@ -1678,6 +1868,7 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
   if (!x_dev || !mod_dev || !x3_out_dev || !s_out_dev || M < 1 || layer < 0 || layer >= NL)
     return h->err.set(LADIFF_ERR_INVALID, "ladiff_ffn_test: bad argument");
   if (fused && mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "ladiff_ffn_test: the fused kernel is a tensor-core path");
+  if (fused && ffn_swap_rt(M) == 0) fused = 0;   // above the co-resident capacity the plans run the separate linears
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DenLayerW& w = h->den[layer];
   const int planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
@@ -1698,8 +1889,7 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
       f.pair[1].W1 = &w.gff1; f.pair[1].W2 = &w.gff2; f.pair[1].act = EPI_GELU; f.pair[1].kind = EPI_LN_MOD_SILU;
       f.pair[1].ln_g = w.ffn_sn_g; f.pair[1].ln_b = w.ffn_sn_b; f.pair[1].mod = mod_dev; f.pair[1].out = sb.act;
       f.dbg = g_ffn_dbg;
-      f.force_cluster = fused == 2;
-      return launch_ffn_cluster(h, st, mode, f);
+      return launch_ffn_swap(h, st, mode, f);
     }
     LinCall c;
     c.A = &x; c.W = &w.ff1; c.M_max = M; c.epi = EPI_RELU; c.out = hb.act; c.out_planes = planes;
@@ -1733,9 +1923,9 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
   CK(cudaStreamSynchronize(st));
   if (fused && getenv("LADIFF_DBG_STAMPS")) {
     long long* dbg = nullptr;
-    const int rt = fused == 2 ? 0 : ffn_swap_rt(M);
-    const int ncta = rt > 0 ? ((M + rt - 1) / rt) * 4 : ((M + 127) / 128) * 8;
-    const int dstride = rt > 0 ? 128 : 48;
+    const int rt = ffn_swap_rt(M);
+    const int ncta = ((M + rt - 1) / rt) * 4;
+    const int dstride = 128;
     CK(ar.alloc((void**)&dbg, ncta * dstride * sizeof(long long)));
     CK(cudaMemsetAsync(dbg, 0, ncta * dstride * sizeof(long long), st));
     g_ffn_dbg = dbg;
@@ -1747,7 +1937,7 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
     // clock64 stamps relative to the CTA start; slot meaning: see the FSTAMP / SSTAMP sites of the kernel (+20 per pair)
     for (int cta : {0, 3, ncta - 1}) {
       const long long* d = hb.data() + cta * dstride;
-      fprintf(stderr, "  %s cta %3d:", rt > 0 ? "swap" : "cluster", cta);
+      fprintf(stderr, "  swap cta %3d:", cta);
       for (int i = 1; i < dstride; ++i)
         if (d[i]) fprintf(stderr, " [%d]%lld", i, d[i] - d[0]);
       fprintf(stderr, "\n");

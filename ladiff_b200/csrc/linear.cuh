@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(256) k_linear_simt(const LinArgs p) {
   }
 }
 
+// A packed weight carries THREE 16-bit planes of n_pad rows: fp16 hi | fp16 lo | bf16 (kernels.cuh k_pack_weight).
+// The x3 mode reads planes 0 and 1, the bf16 mode plane 2.
+template <int NSPLIT>
+__device__ __forceinline__ constexpr int w_plane(int pl) { return NSPLIT == 2 ? pl : 2; }
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 backend
 //
@@ -209,10 +214,6 @@ struct TcCfg {
   static constexpr int TILE_BYTES = 32 * TILE_LD * 4;        // one warp-private 32x32 fp32 tile
   static_assert(8 * TILE_BYTES <= STAGES * STAGE_BYTES, "epilogue tiles must fit in the dead stage memory");
 };
-
-__device__ __forceinline__ uint32_t pack2_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16) | __bfloat16_as_ushort(a);
-}
 
 // slow path: per-thread scalar stores (scatter / unaligned / partial column chunk)
 __device__ __forceinline__ void tc_store32_slow(const LinArgs& p, long drow, int col0, const float (&y)[32]) {
@@ -290,14 +291,14 @@ __device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs
       if (i * 4 + (lane >> 3) < nvalid) *reinterpret_cast<float4*>(d + i * step) = a[i];
   }
   if (p.out.pl && p.out_planes > 0) {
-    __nv_bfloat16* dh = p.out.pl + off0;
-    __nv_bfloat16* dl = dh + static_cast<long>(p.out.rows_alloc) * p.out.ld;
+    op16* dh = p.out.pl + off0;
+    op16* dl = dh + static_cast<long>(p.out.rows_alloc) * p.out.ld;
     const bool two = p.out_planes > 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       uint32_t h01, l01, h23, l23;
-      split2_bf16(a[i].x, a[i].y, h01, l01);
-      split2_bf16(a[i].z, a[i].w, h23, l23);
+      split2_op(a[i].x, a[i].y, p.out_planes, h01, l01);
+      split2_op(a[i].z, a[i].w, p.out_planes, h23, l23);
       if (i * 4 + (lane >> 3) < nvalid) {
         *reinterpret_cast<uint2*>(dh + i * step) = make_uint2(h01, h23);
         if (two) *reinterpret_cast<uint2*>(dl + i * step) = make_uint2(l01, l23);
@@ -347,7 +348,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* st = smem + s * C::STAGE_BYTES;
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl)
-      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
+      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, w_plane<NSPLIT>(pl) * p.w_plane_rows + n0);
   };
   auto produce_a = [&](int kb) {
     const int s = kb % STAGES;
@@ -408,7 +409,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     {
       // ===== MMA issuer (whole warp in the uniform loop, one elected lane issues) =====
-      constexpr uint32_t idesc = tc::idesc_bf16_f32(C::BM, BN);
+      constexpr uint32_t idesc = tc::idesc_op<NSPLIT>(C::BM, BN);
       const uint32_t smem_u = tc::smem_u32(smem);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
@@ -654,7 +655,7 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* st = smem + s * C::STAGE_BYTES;
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl)
-      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, pl * p.w_plane_rows + n0);
+      tc::tma_load_2d(st + NSPLIT * C::A_BYTES + pl * C::W_BYTES, &tmW, &full[s], kb * C::BK, w_plane<NSPLIT>(pl) * p.w_plane_rows + n0);
   };
   auto produce_a = [&](int kb) {
     const int s = kb % STAGES;
@@ -710,7 +711,7 @@ k_linear_tc_ln(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::cluster_sync();
   } else if (warp == 1) {
     {
-      constexpr uint32_t idesc = tc::idesc_bf16_f32(C::BM, BN);
+      constexpr uint32_t idesc = tc::idesc_op<NSPLIT>(C::BM, BN);
       const uint32_t smem_u = tc::smem_u32(smem);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;

@@ -144,6 +144,15 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// the same with fp16 A / B (format code 0)
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// operand format by number of planes (common.cuh op16): 2 planes = fp16 hi / lo split, 1 plane = bf16
+template <int NSPLIT>
+__host__ __device__ constexpr uint32_t idesc_op(int M, int N) {
+  return NSPLIT == 2 ? idesc_f16_f32(M, N) : idesc_bf16_f32(M, N);
+}
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------
 // wait(): blocks until the grids this launch depends on have completed and their memory is visible (no-op without a

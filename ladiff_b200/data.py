@@ -10,11 +10,19 @@ class SyntheticDataModule:
     """Holds (mean, std, nfeats, njoints) like ``HumanML3DDataModule.hparams``; no dataset on disk is needed."""
     accepts_cuda = True
 
-    def __init__(self, nfeats: int = 263, njoints: int = 22, mean=None, std=None, engine=None):
+    def __init__(self, nfeats: int = 263, njoints: int = 22, mean=None, std=None, engine=None, mean_eval=None, std_eval=None):
         self.nfeats, self.njoints = nfeats, njoints
         self.mean = torch.zeros(nfeats) if mean is None else torch.as_tensor(mean, dtype=torch.float32)
         self.std = torch.ones(nfeats) if std is None else torch.as_tensor(std, dtype=torch.float32)
+        self.mean_eval = self.mean if mean_eval is None else torch.as_tensor(mean_eval, dtype=torch.float32)
+        self.std_eval = self.std if std_eval is None else torch.as_tensor(std_eval, dtype=torch.float32)
+        self.is_mm = False
         self._engine = engine
+
+    def renorm4t2m(self, features: torch.Tensor) -> torch.Tensor:
+        """data/HumanML3D.py:57-65: de-normalise with the dataset statistics, re-normalise with the T2M evaluators' ones."""
+        f = features * self.std.to(features) + self.mean.to(features)
+        return (f - self.mean_eval.to(features)) / self.std_eval.to(features)
 
     def bind_engine(self, engine):
         self._engine = engine

@@ -65,6 +65,7 @@ class LADIFF(nn.Module):
             p.requires_grad = False
         self.do_classifier_free_guidance = self.guidance_scale > 1.0
         self.feats2joints = datamodule.feats2joints
+        self.t2m_textencoder = self.t2m_moveencoder = self.t2m_motionencoder = None     # built on first t2m_eval
         self._shared_engine = None
         self._pipe_streams = None
         self.times: List[float] = []
@@ -263,5 +264,61 @@ class LADIFF(nn.Module):
             feats.record_stream(cur)
             yield feats
 
-    def t2m_eval(self, batch):
-        raise NotImplementedError("t2m_eval needs the pretrained T2M evaluators and datasets (SURVEY.md 8f row 3)")
+    @torch.no_grad()
+    def t2m_eval(self, batch, is_mm: bool = False, latents: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
+        """Evaluation glue (reference :1111-1282): stage 'diffusion' samples from the texts, stage 'vae' reconstructs the ground
+        truth through ``vae.encode`` -> ``vae.decode``; both then go through feats2joints, the T2M renormalisation and the T2M
+        co-embedding evaluators.  Returns the reference's dict (m_ref, m_rst, lat_t, lat_m, lat_rm, joints_ref, joints_rst).
+        ``latents`` / ``eps`` inject the random draws (initial noise / rsample) for parity tests."""
+        texts = list(batch["text"])
+        motions = batch["motion"].detach().clone()
+        lengths = [int(x) for x in batch["length"]]
+        word_embs = batch["word_embs"].detach().clone()
+        pos_ohot = batch["pos_ohot"].detach().clone()
+        text_lengths = batch["text_len"].detach().clone()
+        if is_mm:                                                                          # :1123-1134
+            r = self.cfg.TEST.MM_NUM_REPEATS
+            texts, lengths = texts * r, lengths * r
+            motions, word_embs, pos_ohot, text_lengths = (t.repeat_interleave(r, dim=0) for t in (motions, word_embs, pos_ohot, text_lengths))
+        self._bind()
+        if self.stage in ("diffusion", "vae_diffusion"):                                   # :1136-1147
+            if self.do_classifier_free_guidance:
+                uncond = [""] * len(texts)
+                uncond.extend(texts if self.condition == "text" else uncond)
+                text_in = uncond
+            else:
+                text_in = texts
+            z = self._diffusion_reverse(self.text_encoder(text_in), lengths, latents=latents)
+        elif self.stage == "vae":                                                          # :1152-1156
+            z, _, _ = self.vae.encode(motions, lengths, eps=eps)
+            if self.condition == "text_uncond":
+                z = torch.randn_like(z)
+        else:
+            raise NotImplementedError(f"stage {self.stage!r}")
+        feats_rst = self.vae.decode(z, lengths)                                            # :1203
+        # match the ground-truth length (:1218-1229; decode already pads to max(lengths) with zeros)
+        max_len = max(lengths)
+        if feats_rst.shape[1] != max_len:
+            out = feats_rst.new_zeros((feats_rst.shape[0], max_len, feats_rst.shape[2]))
+            n = min(max_len, feats_rst.shape[1])
+            out[:, :n] = feats_rst[:, :n]
+            feats_rst = out
+        motions = motions.to(feats_rst.device)
+        on_gpu = getattr(self.datamodule, "accepts_cuda", False)
+        joints_rst = self.feats2joints(feats_rst if on_gpu else feats_rst.cpu())         # :1245-1246
+        joints_ref = self.feats2joints(motions if on_gpu else motions.cpu())
+        feats_rst = self.datamodule.renorm4t2m(feats_rst)                                  # :1250-1251
+        motions = self.datamodule.renorm4t2m(motions)
+        m_lens = torch.tensor(lengths, device=motions.device)                              # :1254-1261
+        align_idx = torch.argsort(m_lens, descending=True, stable=True)
+        motions, feats_rst, m_lens = motions[align_idx], feats_rst[align_idx], m_lens[align_idx]
+        m_lens = torch.div(m_lens, self.cfg.DATASET.HUMANML3D.UNIT_LEN, rounding_mode="floor")
+        if getattr(self, "t2m_moveencoder", None) is None:
+            from .evaluators import build_t2m_evaluators
+            self.t2m_textencoder, self.t2m_moveencoder, self.t2m_motionencoder = (
+                m.to(motions.device) for m in build_t2m_evaluators(self.cfg, self.nfeats))
+        recons_emb = self.t2m_motionencoder(self.t2m_moveencoder(feats_rst[..., :-4]), m_lens)      # :1263-1266
+        motion_emb = self.t2m_motionencoder(self.t2m_moveencoder(motions[..., :-4]), m_lens)
+        text_emb = self.t2m_textencoder(word_embs.to(motions.device), pos_ohot.to(motions.device), text_lengths)[align_idx]   # :1269-1270
+        return {"m_ref": motions, "m_rst": feats_rst, "lat_t": text_emb, "lat_m": motion_emb, "lat_rm": recons_emb,
+                "joints_ref": joints_ref, "joints_rst": joints_rst}

@@ -99,18 +99,35 @@ class LADiffVae(EngineBound):
         out = self.engine().vae_decode(z, lengths, self.mode, max_len=max_len)
         return out.to(z.dtype)
 
-    def encode(self, features: Tensor, lengths: Optional[List[int]] = None):
-        """reference :162-286 (LAD branch, JOINT_DISTRO_FIX False).  Torch path: not part of sampling."""
+    def encode(self, features: Tensor, lengths: Optional[List[int]] = None, eps: Optional[Tensor] = None,
+               generator: Optional[torch.Generator] = None):
+        """features [B, max(lengths), nfeats] -> (latent [MAX_IT,B,256], dist, max_iter_elements)  (reference :162-286, LAD
+        branch, JOINT_DISTRO_FIX False).  CUDA tensors run in the sm_100a kernels behind ``ladiff_vae_encode`` (ragged
+        token sequence mu | logvar | frames through the non-MD skip encoder); ``dist`` is the same
+        ``torch.distributions.Normal(mu, std)`` on the valid rows (masked rows, whose values nothing reads in the reference,
+        are N(0, 1) here) and ``latent = mu + std * eps`` with ``eps`` injected or drawn from ``generator``."""
         if self.joint_distro_fix or self.dvae:
             raise NotImplementedError("encode supports JOINT_DISTRO_FIX=False, DVAE=False")
         if lengths is None:
             lengths = [len(f) for f in features]
+        lengths = [int(x) for x in lengths]
+        mie = torch.ceil(torch.tensor(lengths) / self.frame_per_latent).to(torch.long)      # :198
+        if not features.is_cuda:
+            return self._encode_torch(features, lengths, mie, eps)
+        if eps is None:
+            eps = torch.randn((self.max_it, len(lengths), self.latent_dim), device=features.device, dtype=torch.float,
+                              generator=generator)
+        latent, mu, std = self.engine().vae_encode(features, lengths, self.mode, eps)
+        return latent.to(features.dtype), torch.distributions.Normal(mu, std), mie
+
+    def _encode_torch(self, features, lengths, mie, eps=None):
+        """Plain-torch statement of the same computation for CPU tensors (host-side tests of the parameter holders; the CUDA
+        path above is the product)."""
         device = features.device
         bs = features.shape[0]
         mask = lengths_to_mask(lengths, device)
         x = self.skel_embedding(features).permute(1, 0, 2)
         dist = torch.tile(self.global_motion_token[:, None, :], (1, bs, 1))
-        mie = torch.ceil(torch.tensor(lengths) / self.frame_per_latent).to(torch.long)
         dm = torch.ones((bs, self.max_it), dtype=torch.bool, device=device)
         for i, e in enumerate(mie):
             dm[i, int(e):] = False
@@ -121,7 +138,7 @@ class LADiffVae(EngineBound):
         mu, logvar = dist[:self.max_it], dist[self.max_it:]
         std = logvar.exp().pow(0.5)
         d = torch.distributions.Normal(mu, std)
-        latent = d.rsample()
+        latent = d.rsample() if eps is None else mu + std * eps
         for i, e in enumerate(mie):
             latent[int(e):, i] = 0
         return latent, d, mie

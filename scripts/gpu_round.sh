@@ -8,12 +8,18 @@ mkdir -p gpurun_out
 for w in $what; do
   case $w in
     tests)
-      timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/${tag}_pytest.log 2>&1
+      timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/${tag}_pytest.log 2>&1
       grep -E "passed|failed|error|measured|max-abs err" gpurun_out/${tag}_pytest.log | tail -60
       python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 ;;
     bench)
       timeout 1200 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
       tail -c 3000 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err ;;
+    quick)   # A/B timing: reverse / decode split + the pipelined bench line without extras
+      python scripts/prof_step.py bf16x3 50 5 128 2>&1 | tail -2
+      timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --quick > gpurun_out/${tag}_quick.json 2>> gpurun_out/${tag}_bench.err
+      python -c "
+import json; d=json.loads([l for l in open('gpurun_out/${tag}_quick.json') if l.startswith('{')][-1])
+print({k: d.get(k) for k in ('value','ms_per_step','latency_ms_per_batch','value_sequential','p50_latency_ms')}, d['e2e']['value'])" ;;
     ref)
       timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_ref.json 2>> gpurun_out/${tag}_bench.err
       head -c 600 gpurun_out/${tag}_ref.json; echo ;;

@@ -1,5 +1,5 @@
-"""The cluster-fused feed-forward kernels (csrc/ffn_swap.cuh: token groups of <= 48 on the MMA N axis, clusters of 4;
-csrc/ffn_cluster.cuh: 128-row tiles, clusters of 8) against a torch fp64 restatement of the two feed-forward
+"""The cluster-fused feed-forward kernel (csrc/ffn_swap.cuh: token groups of <= 48 on the MMA N axis, clusters of 4)
+against a torch fp64 restatement of the two feed-forward
 pairs of a denoiser layer (reference: mdiff_transformer.py:60-62 sa_block FFN + norm2; :137-162,248-262 FFN + StylizationBlock
 prologue), and against the four separate fused linears it replaces."""
 import pytest
@@ -29,31 +29,28 @@ def ref_ffn(sd, layer, x, mod):
 
 @pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
 @pytest.mark.parametrize("M,layer", [(1280, 0), (128, 4), (77, 8), (1, 2), (300, 5), (2000, 7)])
-def test_ffn_cluster(engine, oracle_sd, mode, M, layer):
+def test_ffn_fused(engine, oracle_sd, mode, M, layer):
     from ladiff_b200._lib import MODES
     g = torch.Generator(device="cpu").manual_seed(M * 31 + layer)
     x = torch.randn((M, 256), generator=g)
     mod = 0.3 * torch.randn((512,), generator=g)
     x3r, sr = ref_ffn(oracle_sd, layer, x, mod)
     x3, s, _ = engine.ffn_test(x.cuda(), layer, mod.cuda(), mode=MODES[mode], fused=True)    # k_ffn_swap for M <= 1776
-    x3c, sc, _ = engine.ffn_test(x.cuda(), layer, mod.cuda(), mode=MODES[mode], fused=2)      # k_ffn_cluster
     x3u, su, _ = engine.ffn_test(x.cuda(), layer, mod.cuda(), mode=MODES[mode], fused=False)
     assert torch.isfinite(x3).all() and torch.isfinite(s).all()
-    for name, got, ref in (("x3", x3, x3r), ("s", s, sr), ("x3 cluster", x3c, x3r), ("s cluster", sc, sr),
-                           ("x3 unfused", x3u, x3r), ("s unfused", su, sr)):
+    for name, got, ref in (("x3", x3, x3r), ("s", s, sr), ("x3 unfused", x3u, x3r), ("s unfused", su, sr)):
         err = (got.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
         assert err < TOL[mode], f"{mode} M={M} layer={layer} {name}: rel max err {err:.3e}"
 
 
-def test_ffn_cluster_deterministic(engine):
+def test_ffn_fused_deterministic(engine):
     from ladiff_b200._lib import MODES
     g = torch.Generator(device="cpu").manual_seed(5)
     x = torch.randn((1280, 256), generator=g).cuda()
     mod = (0.3 * torch.randn((512,), generator=g)).cuda()
-    for fused in (True, 2):
-        a = engine.ffn_test(x, 3, mod, mode=MODES["bf16x3"], fused=fused)
-        b = engine.ffn_test(x, 3, mod, mode=MODES["bf16x3"], fused=fused)
-        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])   # fixed-order reduce-scatter: bit-reproducible
+    a = engine.ffn_test(x, 3, mod, mode=MODES["bf16x3"], fused=True)
+    b = engine.ffn_test(x, 3, mod, mode=MODES["bf16x3"], fused=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])   # fixed-order reduce-scatter: bit-reproducible
 
 
 @pytest.mark.parametrize("rt", [16, 32, 48])
