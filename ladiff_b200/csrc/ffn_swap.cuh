@@ -59,6 +59,8 @@ struct FfnArgs {
   Act att_x1;                      // fp32 master of x1 (residual of pair 0)
   Act att_xcopy;                   // optional copy of the layer input (U-Net skip source), fp32 and/or planes
   int w1_plane_rows[2], w2_plane_rows[2];
+  const uint8_t* w1_img[2];   // streaming images of the pair's weights in this mode (k_pack_swap_image): [rank][8 stages][STG bytes]
+  const uint8_t* w2_img[2];
   unsigned long long* trace;
   long long* dbg;        // optional per-CTA clock64 stamps [ncta][128] (ladiff_ffn_test with LADIFF_DBG_STAMPS=1)
 };
@@ -70,7 +72,11 @@ struct SwapCfg {
   static constexpr int STG = NSPLIT * U;       // ring stage: all planes of one weight block
   static constexpr int RT_MAX = 48;
   static constexpr int EPI_WARPS = 8, THREADS = 64 + EPI_WARPS * 32;
-  static constexpr int TMEM_COLS = 256;        // acc A: [0, 2 RT)   acc B: [2 RT, 4 RT)
+  // x3 mode: the B operand of one MMA is [x_hi ; x_lo] (the two planes are adjacent in shared memory, same 128-byte row pitch), so
+  // an accumulator tile is AW = 2 RT columns wide: [0, RT) = w_hi.x_hi + w_lo.x_hi, [RT, 2 RT) = w_hi.x_lo; summed by its reader.
+  // Two MMAs per k-step instead of three, and the 4 KB weight tile is fetched from shared memory twice instead of three times
+  // (the N = 48 MMAs are bound by that fetch, not by the tensor pipe: scripts/micro/mma_small_n_probe.cu).
+  static constexpr int TMEM_COLS = NSPLIT == 2 ? 512 : 256;   // acc A: [0, 2 AW)   acc B: [2 AW, 4 AW)
   static constexpr int SMEM_LIMIT = 227 * 1024;
   static constexpr int TAIL = 512 /*barriers*/ + 1024 /*alignment slack*/;
   __host__ __device__ static constexpr int op_bytes(int rt) { return 4 * NSPLIT * rt * 128; }   // [kb][plane][rt x 128 B]
@@ -107,6 +113,10 @@ __device__ __forceinline__ void cluster_sync_relaxed() {
 }
 __device__ __forceinline__ void st_cluster_v2u(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_shared_v2u(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 // generic-proxy writes (st.shared / st.shared::cluster) -> visible to the async proxy (tcgen05.mma operand reads), all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -307,6 +317,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   constexpr int U = C::U, STG = C::STG;
   const int M = p.M_dev ? min(p.M_max, *p.M_dev) : p.M_max;
   const int rt = p.rt, tpc = rt >> 2;       // tokens per cluster / owned per CTA
+  const int aw = NSPLIT == 2 ? 2 * rt : rt; // accumulator tile width (TMEM columns)
   const int row0 = blockIdx.x * rt;
   tc::pdl_launch_dependents();
   if (row0 >= M) return;  // cluster-uniform
@@ -338,34 +349,17 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 
   auto issue_load = [&](int j) {
     // stage r of a pair: r < 8 phase A (M tile g = r >> 2, k-block r & 3); r >= 8 phase B ordered by the availability of h:
-    // first every (out tile, k-block) that reads hidden M tile 0 (k-blocks 0, 1), then those reading tile 1 (k-blocks 2, 3)
-    const int slot = j & 3, pr = j >> 4, r = j & 15, ph = r >> 3;
-    const int g = ph ? (r >> 1) & 1 : (r >> 2) & 1, kb = ph ? ((r >> 2) & 1) * 2 + (r & 1) : r & 3;
-    const CUtensorMap* m;
-    int kcol, row, prow;
-    if (ph == 0) {
-      m = pr == 0 ? &tmW1a : &tmW1b;
-      kcol = kb * C::BK;
-      row = static_cast<int>(rank) * C::HS + g * 128;
-      prow = p.w1_plane_rows[pr];
-    } else {
-      m = pr == 0 ? &tmW2a : &tmW2b;
-      kcol = static_cast<int>(rank) * C::HS + kb * C::BK;
-      row = g * 128;
-      prow = p.w2_plane_rows[pr];
-    }
+    // first every (out tile, k-block) that reads hidden M tile 0 (k-blocks 0, 1), then those reading tile 1 (k-blocks 2, 3).
+    // The streaming image holds the stages of a (weight, rank) in exactly that order: one contiguous bulk copy per stage.
+    const int slot = j & 3, pr = j >> 4, r = j & 15;
+    const uint8_t* src = (r < 8 ? p.w1_img[pr] : p.w2_img[pr]) + (static_cast<size_t>(rank) * 8 + (r & 7)) * STG;
     tc::mbar_expect_tx(&full[slot], STG);
-#pragma unroll
-    for (int pl = 0; pl < NSPLIT; ++pl) tc::tma_load_2d(ring + slot * STG + pl * U, m, &full[slot], kcol, w_plane<NSPLIT>(pl) * prow + row);
+    tc::bulk_load_1d(ring + slot * STG, src, STG, &full[slot]);
   };
 
   if (warp == 0) {
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmX);
-      tc::tma_prefetch_desc(&tmW1a);
-      tc::tma_prefetch_desc(&tmW2a);
-      tc::tma_prefetch_desc(&tmW1b);
-      tc::tma_prefetch_desc(&tmW2b);
       for (int i = 0; i < 4; ++i) {
         tc::mbar_init(&full[i], 1);
         tc::mbar_init(&empty[i], 1);
@@ -427,7 +421,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
-    const uint32_t idesc = tc::idesc_op<NSPLIT>(128, rt);
+    const uint32_t idesc = tc::idesc_op<NSPLIT>(128, rt), idesc_cat = tc::idesc_op<NSPLIT>(128, 2 * rt);
     const uint32_t ring_u = tc::smem_u32(ring), xop_u = tc::smem_u32(xop), hr_u = tc::smem_u32(hr);
     const uint32_t tmem_u = tmem_base;
     if (ATT) {
@@ -452,7 +446,7 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           if (r == 0) SSTAMP(2 + 20 * pr);
           if (r == 8) SSTAMP(3 + 20 * pr);
         }
-        const uint32_t d = tmem_u + (ph ? 2 * rt : 0) + g * rt;
+        const uint32_t d = tmem_u + (ph ? 2 * aw : 0) + g * aw;
         const uint32_t sw = ring_u + slot * STG;
         const uint32_t sx = (ph ? hr_u : xop_u) + kb * NSPLIT * XT;
         if (tc::elect_one()) {
@@ -464,10 +458,9 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             if (NSPLIT == 1) {
               tc::mma_bf16_ss(d, w_hi, x_hi, idesc, acc0);
             } else {
-              const uint64_t w_lo = tc::smem_desc_sw128(sw + U + koff), x_lo = tc::smem_desc_sw128(sx + XT + koff);
-              tc::mma_bf16_ss(d, w_hi, x_lo, idesc, acc0);
+              const uint64_t w_lo = tc::smem_desc_sw128(sw + U + koff);
+              tc::mma_bf16_ss(d, w_hi, x_hi, idesc_cat, acc0);   // N = 2 rt: x_hi rows, then the x_lo plane right behind them
               tc::mma_bf16_ss(d, w_lo, x_hi, idesc, 1u);
-              tc::mma_bf16_ss(d, w_hi, x_hi, idesc, 1u);
             }
           }
           tc::mma_commit(&empty[slot]);
@@ -553,7 +546,13 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           for (int c = 0; c < nch; ++c) {
             float v[8];
             const int t0 = tok0 + c * 8;               // multiple of 8: token t0 + k sits in row k of 8-row group t0 / 8
-            tmem_ld8(tmem_base + tlane + gt * rt + t0, v);
+            tmem_ld8(tmem_base + tlane + gt * aw + t0, v);
+            if (NSPLIT == 2) {
+              float v2[8];
+              tmem_ld8(tmem_base + tlane + gt * aw + rt + t0, v2);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] += v2[k];
+            }
             uint8_t* hrow = hb + (t0 >> 3) * 1024;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -596,18 +595,29 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       if (e == 0 && lane == 0) SSTAMP(11 + 20 * pr);
       {
         const uint32_t mine = (rank * tpc * C::D + f) * 4;
+        // this CTA's own tokens take the plain shared-memory path: a st.shared::cluster to the own rank still travels through the
+        // SM-to-SM network, whose ~16 B/clk per SM is what bounds this exchange
         int dst = 0, tl = 0;
-        uint32_t base = tc::mapa(recv_local, 0) + mine;
+        bool self = rank == 0;
+        uint32_t base = (self ? recv_local : tc::mapa(recv_local, 0)) + mine;
         for (int c = 0; c < rt / 16; ++c) {
           float v[16];
-          tmem_ld16(tmem_base + tlane + 2 * rt + g * rt + c * 16, v);
+          tmem_ld16(tmem_base + tlane + 2 * aw + g * aw + c * 16, v);
+          if (NSPLIT == 2) {
+            float v2[16];
+            tmem_ld16(tmem_base + tlane + 2 * aw + g * aw + rt + c * 16, v2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] += v2[k];
+          }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            tc::st_cluster_f32(base + tl * (C::D * 4), v[k]);
+            if (self) st_shared_f32(base + tl * (C::D * 4), v[k]);
+            else tc::st_cluster_f32(base + tl * (C::D * 4), v[k]);
             if (++tl == tpc) {
               tl = 0;
               ++dst;
-              base = tc::mapa(recv_local, dst & 3) + mine;
+              self = static_cast<uint32_t>(dst & 3) == rank;
+              base = (self ? recv_local : tc::mapa(recv_local, dst & 3)) + mine;
             }
           }
         }
@@ -684,13 +694,18 @@ k_ffn_swap(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           // next X operand into every CTA of the cluster: k-block j, 8 bytes inside swizzle chunk (c0 >> 3)
           const uint32_t rowoff = (otcl >> 3) * 1024 + (otcl & 7) * 128 + ((((c0 >> 3) ^ (otcl & 7)) << 4) | ((c0 & 7) * 2));
 #pragma unroll
-          for (int k = 0; k < C::CL; ++k) {
-            const uint32_t base = tc::mapa(xop_local, k) + rowoff;
+          for (int k = 1; k < C::CL; ++k) {   // the three peers first (the slow path), then the own copy through plain st.shared
+            const uint32_t base = tc::mapa(xop_local, (rank + k) & 3) + rowoff;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               st_cluster_v2u(base + (j * NSPLIT) * XT, hi2[j].x, hi2[j].y);
               if (NSPLIT == 2) st_cluster_v2u(base + (j * NSPLIT + 1) * XT, lo2[j].x, lo2[j].y);
             }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st_shared_v2u(xop_local + rowoff + (j * NSPLIT) * XT, hi2[j].x, hi2[j].y);
+            if (NSPLIT == 2) st_shared_v2u(xop_local + rowoff + (j * NSPLIT + 1) * XT, lo2[j].x, lo2[j].y);
           }
         }
         if (e == 0 && lane == 0) SSTAMP(16 + 20 * pr);

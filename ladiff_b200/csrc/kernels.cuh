@@ -603,58 +603,143 @@ __global__ void k_gather_z(const float* __restrict__ z, const int* __restrict__ 
   if (t < m) act_store(out, planes, moff[b] + t, c, z[(static_cast<long>(t) * B + b) * 256 + c]);
 }
 
-// cross-attention to the <= MAXT valid latent rows of the sequence (operator/cross_attention.py:373-376):
-// one warp per frame row; lane owns 8 dims, 8 lanes per head.
+// Decoder cross-attention block (operator/cross_attention.py:373-377, 408-409: multihead_attn(q = tgt, k = v = memory, key-padding =
+// the m_i <= 5 valid latents) -> + residual -> norm2) as ONE kernel.  With so few keys the two projections around the attention are
+// folded into the per-sequence memory table at weight-load / table-build time (exact algebra, products formed in fp64):
+//     score_hj = (x . kq_hj + cq_hj) / 8      kq_hj = W_q[h]^T k_hj  (256-vector),  cq_hj = b_q[h] . k_hj
+//     out      = b_o + sum_h sum_j softmax_j(score_h.) v'_hj              v'_hj = W_o[:, h] v_hj  (256-vector)
+// so neither the query GEMM nor the out-projection GEMM exists any more: per frame 2 x 20 dot / axpy operations of length 256
+// in fp32 plus the LayerNorm.  Table row of a memory latent, per layer (CX_LD floats): kq[4][256] | v'[4][256] | cq[4] | pad.
+// CTA = (32 frames, sequence): the sequence's table rows (<= 42 KB) are staged in shared memory once, a warp owns 4 consecutive
+// frames so that every table value it reads is used four times; lane <-> 8 consecutive columns; heads are processed one at a time
+// (20 live scores instead of 80) so that two CTAs fit per SM.
+#define CX_LD 2112
 template <int MAXT>
-__global__ void k_attn_cross(const float* __restrict__ q, const float* __restrict__ memkv, int ld_memkv, int kv_off,
-                             const int* __restrict__ row_seq, const int* __restrict__ moff,
-                             const int* __restrict__ R_dev, Act out, int planes) {
+__global__ void __launch_bounds__(256, 2) k_cross_ln(const float* __restrict__ x, const float* __restrict__ tab, int ld_tab, int tab_off,
+                                                     const int* __restrict__ foff, const int* __restrict__ moff,
+                                                     const float* __restrict__ bo, const float* __restrict__ g,
+                                                     const float* __restrict__ bvec, Act out, int planes) {
+  constexpr int F = 4;
+  extern __shared__ float cx_tab[];                      // [m][CX_LD]: this sequence's table rows of this layer
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f0 = blockIdx.x * 32 + warp * F;
+  const int c0 = lane * 8;
+  float4 bo4[2], g4[2], b4[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    bo4[q] = __ldg(reinterpret_cast<const float4*>(bo + c0) + q);
+    g4[q] = __ldg(reinterpret_cast<const float4*>(g + c0) + q);
+    b4[q] = __ldg(reinterpret_cast<const float4*>(bvec + c0) + q);
+  }
   pdl_prologue();
-  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= *R_dev) return;
-  const int b = row_seq[row];
+  const int r0 = foff[b], L = foff[b + 1] - r0;
+  if (static_cast<int>(blockIdx.x) * 32 >= L) return;    // CTA-uniform
   const int m0 = moff[b], m = min(moff[b + 1] - m0, MAXT);
-  const int d = lane * 8;
-  float qv[8];
-  {
-    const float4 a = *reinterpret_cast<const float4*>(q + row * 256 + d);
-    const float4 c = *reinterpret_cast<const float4*>(q + row * 256 + d + 4);
-    qv[0] = a.x * 0.125f; qv[1] = a.y * 0.125f; qv[2] = a.z * 0.125f; qv[3] = a.w * 0.125f;
-    qv[4] = c.x * 0.125f; qv[5] = c.y * 0.125f; qv[6] = c.z * 0.125f; qv[7] = c.w * 0.125f;
-  }
-  float sc[MAXT], mx = -INFINITY;
+  // ---- the table (kq | v' | cq of the m latents) and this warp's four frames: one global round trip for the whole CTA
+  float xv[F][8];
 #pragma unroll
-  for (int j = 0; j < MAXT; ++j) {
-    float p = 0.f;
-    if (j < m) {
-      const float* kp = memkv + static_cast<long>(m0 + j) * ld_memkv + kv_off + d;
-      const float4 a = *reinterpret_cast<const float4*>(kp);
-      const float4 c = *reinterpret_cast<const float4*>(kp + 4);
-      p = qv[0] * a.x + qv[1] * a.y + qv[2] * a.z + qv[3] * a.w + qv[4] * c.x + qv[5] * c.y + qv[6] * c.z + qv[7] * c.w;
+  for (int f = 0; f < F; ++f) {
+    const bool on = f0 + f < L;
+    const float4* xp = reinterpret_cast<const float4*>(x + static_cast<long>(r0 + f0 + f) * 256 + c0);
+    const float4 a = on ? xp[0] : make_float4(0.f, 0.f, 0.f, 0.f), c = on ? xp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    xv[f][0] = a.x; xv[f][1] = a.y; xv[f][2] = a.z; xv[f][3] = a.w; xv[f][4] = c.x; xv[f][5] = c.y; xv[f][6] = c.z; xv[f][7] = c.w;
+  }
+  for (int i = threadIdx.x; i < m * (CX_LD / 4); i += 256) {
+    const int j = i / (CX_LD / 4), c4 = i % (CX_LD / 4);
+    reinterpret_cast<float4*>(cx_tab)[i] = __ldg(reinterpret_cast<const float4*>(tab + static_cast<long>(m0 + j) * ld_tab + tab_off) + c4);
+  }
+  __syncthreads();
+  if (f0 >= L) return;                                   // warp-uniform (after the only CTA barrier)
+  // ---- y = x + b_o + sum_h sum_j softmax_j((x . kq_hj + cq_hj) / 8) v'_hj, one head at a time
+  float y[F][8];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    y[f][0] = xv[f][0] + bo4[0].x; y[f][1] = xv[f][1] + bo4[0].y; y[f][2] = xv[f][2] + bo4[0].z; y[f][3] = xv[f][3] + bo4[0].w;
+    y[f][4] = xv[f][4] + bo4[1].x; y[f][5] = xv[f][5] + bo4[1].y; y[f][6] = xv[f][6] + bo4[1].z; y[f][7] = xv[f][7] + bo4[1].w;
+  }
+#pragma unroll 1
+  for (int h = 0; h < 4; ++h) {
+    float sc[F][MAXT];
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      if (j < m) {                                       // warp-uniform
+        const float* row = cx_tab + j * CX_LD + h * 256 + c0;
+        const float4 a = *reinterpret_cast<const float4*>(row), c = *reinterpret_cast<const float4*>(row + 4);
+        const float cq = cx_tab[j * CX_LD + 2048 + h];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          float p = xv[f][0] * a.x;
+          p = fmaf(xv[f][1], a.y, p); p = fmaf(xv[f][2], a.z, p); p = fmaf(xv[f][3], a.w, p);
+          p = fmaf(xv[f][4], c.x, p); p = fmaf(xv[f][5], c.y, p); p = fmaf(xv[f][6], c.z, p); p = fmaf(xv[f][7], c.w, p);
+          sc[f][j] = (warp_sum(p) + cq) * 0.125f;
+        }
+      } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) sc[f][j] = -INFINITY;
+      }
     }
-    p += __shfl_xor_sync(0xffffffffu, p, 1);
-    p += __shfl_xor_sync(0xffffffffu, p, 2);
-    p += __shfl_xor_sync(0xffffffffu, p, 4);
-    sc[j] = (j < m) ? p : -INFINITY;
-    mx = fmaxf(mx, sc[j]);
-  }
-  float den = 0.f, o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-  for (int j = 0; j < MAXT; ++j) {
-    if (j < m) {
-      const float p = expf(sc[j] - mx);
-      den += p;
-      const float* vp = memkv + static_cast<long>(m0 + j) * ld_memkv + kv_off + 256 + d;
-      const float4 a = *reinterpret_cast<const float4*>(vp);
-      const float4 c = *reinterpret_cast<const float4*>(vp + 4);
-      o[0] += p * a.x; o[1] += p * a.y; o[2] += p * a.z; o[3] += p * a.w;
-      o[4] += p * c.x; o[5] += p * c.y; o[6] += p * c.z; o[7] += p * c.w;
+    for (int f = 0; f < F; ++f) {
+      float mx = sc[f][0];
+#pragma unroll
+      for (int j = 1; j < MAXT; ++j) mx = fmaxf(mx, sc[f][j]);
+      float den = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j) {
+        sc[f][j] = (j < m) ? expf(sc[f][j] - mx) : 0.f;
+        den += sc[f][j];
+      }
+      const float inv = 1.0f / den;
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j) sc[f][j] *= inv;
+    }
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      if (j < m) {
+        const float* row = cx_tab + j * CX_LD + 1024 + h * 256 + c0;
+        const float4 a = *reinterpret_cast<const float4*>(row), c = *reinterpret_cast<const float4*>(row + 4);
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float p = sc[f][j];
+          y[f][0] = fmaf(p, a.x, y[f][0]); y[f][1] = fmaf(p, a.y, y[f][1]); y[f][2] = fmaf(p, a.z, y[f][2]); y[f][3] = fmaf(p, a.w, y[f][3]);
+          y[f][4] = fmaf(p, c.x, y[f][4]); y[f][5] = fmaf(p, c.y, y[f][5]); y[f][6] = fmaf(p, c.z, y[f][6]); y[f][7] = fmaf(p, c.w, y[f][7]);
+        }
+      }
     }
   }
-  const float inv = 1.0f / den;
+  // ---- LayerNorm (exact two-pass) and store: fp32 master + operand planes
 #pragma unroll
-  for (int j = 0; j < 8; ++j) act_store(out, planes, row, d + j, o[j] * inv);
+  for (int f = 0; f < F; ++f) {
+    if (f0 + f >= L) break;                              // warp-uniform
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += y[f][k];
+    const float mean = warp_sum(s) * (1.f / 256.f);
+    float q2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = y[f][k] - mean;
+      q2 += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.f / 256.f) + LD_EPS);
+    const float gg[8] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w};
+    const float bb[8] = {b4[0].x, b4[0].y, b4[0].z, b4[0].w, b4[1].x, b4[1].y, b4[1].z, b4[1].w};
+    float z[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z[k] = (y[f][k] - mean) * rstd * gg[k] + bb[k];
+    const long o = static_cast<long>(r0 + f0 + f) * out.ld + c0;
+    if (out.f32) {
+      *reinterpret_cast<float4*>(out.f32 + o) = make_float4(z[0], z[1], z[2], z[3]);
+      *reinterpret_cast<float4*>(out.f32 + o + 4) = make_float4(z[4], z[5], z[6], z[7]);
+    }
+    if (out.pl && planes > 0) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split2_op(z[2 * k], z[2 * k + 1], planes, hi[k], lo[k]);
+      *reinterpret_cast<uint4*>(out.pl + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (planes > 1) *reinterpret_cast<uint4*>(out.pl + static_cast<long>(out.rows_alloc) * out.ld + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
 }
 
 // Ragged self-attention over the L valid frames of one sequence (operator/cross_attention.py:367-369), fp32.
@@ -955,6 +1040,35 @@ __global__ void k_pack_weight(const float* __restrict__ W, int ldw, int N, int K
   pl[2 * static_cast<long>(n_pad) * K + i] = b;
 }
 
+// Streaming image of a 256 -> 1024 -> 256 feed-forward weight for k_ffn_swap: the weight ring of that kernel is filled by ONE contiguous
+// cp.async.bulk per stage instead of one 2-D tensor box per plane (per-SM ingest from L2: 2-D boxes 41 - 48 B/clk, contiguous 32 KB
+// copies 64 B/clk and more: scripts/micro/tma_ingest_probe.cu), so every stage is stored exactly as it has to land in shared memory:
+// 16 KB blocks of [128 weight rows x 64 k] 16-bit elements, K-major, 16-byte chunks XOR-swizzled by (row & 7) (what TMA's 128-byte
+// swizzle would have written), in the order the kernel consumes them:
+//   which = 0 (W1 [1024, 256], phase A): block (rank, g, kb)   = rows rank 256 + g 128 .., k-block kb;         index (rank, g 4 + kb)
+//   which = 1 (W2 [256, 1024], phase B): block (rank, e)  with g = (e >> 1) & 1, kb = ((e >> 2) & 1) 2 + (e & 1)
+//                                         = output rows g 128 .., k-block rank 4 + kb   (ordered by the availability of the hidden tiles)
+// Layout: x3 image [rank][idx][hi | lo] (32 KB stages), then the bf16 image [rank][idx] (16 KB stages).  `pl` = the three planes
+// [3][n_pad][K] of k_pack_weight (fp16 hi | fp16 lo | bf16).
+__global__ void k_pack_swap_image(const op16* __restrict__ pl, int n_pad, int K, int which, op16* __restrict__ img) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one thread per image element: [3 planes][32 blocks][128][64]
+  if (i >= 3L * 32 * 128 * 64) return;
+  const int c = i & 63, r = (i >> 6) & 127, blk = (i >> 13) & 31, plane = static_cast<int>(i >> 18);
+  const int rank = blk >> 3, e = blk & 7;
+  int n, k;
+  if (which == 0) {
+    n = rank * 256 + (e >> 2) * 128 + r;
+    k = (e & 3) * 64 + c;
+  } else {
+    n = ((e >> 1) & 1) * 128 + r;
+    k = rank * 256 + (((e >> 2) & 1) * 2 + (e & 1)) * 64 + c;
+  }
+  const op16 v = pl[(static_cast<long>(plane) * n_pad + n) * K + k];
+  const long in_block = r * 64 + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7));   // element offset inside the 16 KB block
+  const long dst = plane < 2 ? (static_cast<long>(blk) * 2 + plane) * 8192 + in_block : 64L * 8192 + static_cast<long>(blk) * 8192 + in_block;
+  img[dst] = v;
+}
+
 // Weight folding at load time (finalize): C[n, k2] = sum_k1 A[n, k1] * B[k1, k2]  (fp32 in, fp64 accumulate, fp32 out).
 // Used to pre-multiply consecutive nn.Linear weights ([out, in] row-major: y = x W^T, so (W_b W_a) applies a then b).
 __global__ void k_fold_matmul(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int N, int K1,
@@ -974,6 +1088,16 @@ __global__ void k_fold_matvec(const float* __restrict__ A, int lda, const float*
   double acc = b ? static_cast<double>(b[n]) : 0.0;
   for (int k = 0; k < K; ++k) acc += static_cast<double>(A[static_cast<long>(n) * lda + k]) * static_cast<double>(v[k]);
   out[n] = static_cast<float>(acc);
+}
+// C[n, k2] = sum_k1 A[k1, n] * B[k1, k2]   (A^T B; fp64 accumulate) -- folds a query projection into the keys it meets
+__global__ void k_fold_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int N, int K1, int K2,
+                          float* __restrict__ C, int ldc) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(N) * K2) return;
+  const int n = i / K2, k2 = i % K2;
+  double acc = 0.0;
+  for (int k = 0; k < K1; ++k) acc += static_cast<double>(A[static_cast<long>(k) * lda + n]) * static_cast<double>(B[static_cast<long>(k) * ldb + k2]);
+  C[static_cast<long>(n) * ldc + k2] = static_cast<float>(acc);
 }
 // dst[r, c] = (r == c) : rows x rows identity block written into a wider matrix
 __global__ void k_set_identity(float* __restrict__ dst, int ldd, int n) {

@@ -17,6 +17,8 @@
 #include "kernels.cuh"
 #include "linear.cuh"
 #include "ffn_swap.cuh"
+#include "attn_tc5.cuh"
+#include "ffn_tile.cuh"
 
 namespace {
 
@@ -72,6 +74,7 @@ struct Weight {
   float* Wt = nullptr;
   op16* pl = nullptr;
   float* bias = nullptr;
+  op16* swap_img = nullptr;           // k_ffn_swap streaming image (k_pack_swap_image): x3 stages, then bf16 stages; FFN shapes only
   CUtensorMap map64, map128, map256;  // TMA boxes of 64 / 128 / 256 weight rows (one load per plane and k-block)
 };
 
@@ -104,8 +107,9 @@ struct DenLayerW {
   float *n1g, *n1b, *n2g, *n2b, *ca_tn_g, *ca_tn_b, *ca_sn_g, *ca_sn_b, *ffn_sn_g, *ffn_sn_b;
 };
 struct DecLayerW {
-  Weight qkv, out, q2, out2, ff1, ff2;
+  Weight qkv, out, ff1, ff2;
   float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
+  float* out2_bias = nullptr;   // multihead_attn.out_proj.bias (the projections themselves are folded into memx_all)
 };
 
 struct EncLayerW {
@@ -140,7 +144,7 @@ struct ladiff_handle {
   float *den_fg = nullptr, *den_fb = nullptr, *den_pe = nullptr;
   // decoder
   DecLayerW dec[NL];
-  Weight dec_skip[4], dec_final, memkv_all;
+  Weight dec_skip[4], dec_final, memx_all;   // memx_all: folded cross-attention table projection, [9 x CX_LD, 256] (k_cross_ln)
   float *dec_fg = nullptr, *dec_fb = nullptr, *dec_pe = nullptr;
   // LA-VAE encoder (packed with the decoder when its keys are present)
   EncLayerW enc[NL];
@@ -459,6 +463,10 @@ int launch_ffn_swap(H* h, cudaStream_t st, int mode, const FfnCall& c) {
     a.out[i] = q.out;
     a.w1_plane_rows[i] = q.W1->n_pad;
     a.w2_plane_rows[i] = q.W2->n_pad;
+    if (!q.W1->swap_img || !q.W2->swap_img) return h->err.set(LADIFF_ERR_INVALID, "ffn swap: pair %d has no streaming image", i);
+    const size_t img_off = mode == LADIFF_MODE_BF16X3 ? 0 : 64ull * 8192;   // elements: the bf16 stages follow the x3 stages
+    a.w1_img[i] = reinterpret_cast<const uint8_t*>(q.W1->swap_img + img_off);
+    a.w2_img[i] = reinterpret_cast<const uint8_t*>(q.W2->swap_img + img_off);
   }
   a.res = c.res;
   a.addv = c.addv;
@@ -497,6 +505,69 @@ int launch_ffn_swap(H* h, cudaStream_t st, int mode, const FfnCall& c) {
   CK(launch_pdl(kern, grid, dim3(SwapCfg<2>::THREADS), smem, st, mx, q0.W1->map128, q0.W2->map128, q1.W1->map128,
                 q1.W2->map128, a));
   h->launches++;
+  return LADIFF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused feed-forward block on persistent 128-row tiles (ffn_tile.cuh): Linear(256 -> 1024) -> act -> Linear(1024 -> 256) -> LN kind
+struct FtCall {
+  const ActBuf* X = nullptr;
+  const Weight *W1 = nullptr, *W2 = nullptr;
+  int M_max = 0;
+  const int* M_dev = nullptr;
+  int act = EPI_GELU, kind = EPI_LN;
+  const float *ln_g = nullptr, *ln_b = nullptr, *res = nullptr, *addv = nullptr, *mod = nullptr;
+  const int* add_idx = nullptr;
+  int ld_add = 256;
+  Act out{nullptr, nullptr, 0, 0};
+  int out_planes = 0;
+};
+
+bool ffn_tile_enabled(int mode) { return mode != LADIFF_MODE_FP32 && getenv("LADIFF_NO_FFN_TILE") == nullptr; }
+
+int launch_ffn_tile(H* h, cudaStream_t st, int mode, const FtCall& c) {
+  if (mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "the fused feed-forward tile kernel is a tensor-core path");
+  if (!c.X || !c.X->has_map || c.X->act.ld != 256 || !c.W1 || !c.W2 || c.W1->N != 1024 || c.W1->K != 256 || c.W2->N != 256 || c.W2->K != 1024 ||
+      c.out.ld != 256 || (c.kind != EPI_LN && c.kind != EPI_LN_MOD_SILU) || (c.act != EPI_RELU && c.act != EPI_GELU))
+    return h->err.set(LADIFF_ERR_INVALID, "ffn tile: bad operands (256 -> 1024 -> 256 blocks with a LayerNorm-kind epilogue only)");
+  if (c.M_max <= 0) return LADIFF_OK;
+  FtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M_max = c.M_max; a.M_dev = c.M_dev;
+  a.b1 = c.W1->bias; a.b2 = c.W2->bias;
+  a.act = c.act; a.kind = c.kind;
+  a.ln_g = c.ln_g; a.ln_b = c.ln_b; a.res = c.res; a.addv = c.addv; a.add_idx = c.add_idx; a.ld_add = c.ld_add; a.mod = c.mod;
+  a.out = c.out; a.out_planes = c.out_planes;
+  a.x_plane_rows = c.X->act.rows_alloc; a.w1_plane_rows = c.W1->n_pad; a.w2_plane_rows = c.W2->n_pad;
+  const int tiles = (c.M_max + 127) / 128;
+  dim3 grid(tiles < 148 ? tiles : 148);
+  static int dbg_left = getenv("LADIFF_FT_DBG") ? 1 : 0;     // profiling: clock stamps of CTA 0 of the first launch (needs LADIFF_NO_GRAPH=1)
+  long long* dbg = nullptr;
+  if (dbg_left > 0) {
+    CK(cudaMalloc(&dbg, 256 * sizeof(long long)));
+    CK(cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), st));
+    a.dbg = dbg;
+  }
+  if (mode == LADIFF_MODE_BF16X3)
+    CK(launch_pdl(k_ffn_tile<2>, grid, dim3(FtCfg<2>::THREADS), FtCfg<2>::SMEM_BYTES, st, c.X->map, c.W1->map128, c.W2->map128, a));
+  else
+    CK(launch_pdl(k_ffn_tile<1>, grid, dim3(FtCfg<1>::THREADS), FtCfg<1>::SMEM_BYTES, st, c.X->map, c.W1->map128, c.W2->map128, a));
+  h->launches++;
+  if (dbg) {
+    long long hb[256];
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    --dbg_left;
+    fprintf(stderr, "  ffn_tile cta 0 clk: x_full %lld | acco_full %lld | epilogue-0 done %lld | tile-1 x_full %lld | tile-1 acco_full %lld | epilogue-1 done %lld | end %lld\n   mma [wait-acch_empty g1-issued wait-h_full g2-issued] per chunk:", hb[1] - hb[0], hb[2] - hb[0], hb[4] - hb[0], hb[5] - hb[0], hb[6] - hb[0], hb[7] - hb[0], hb[3] - hb[0]);
+    for (int j = 0; j < 8; ++j) fprintf(stderr, " | %lld %lld %lld %lld", hb[8 + 4 * j] ? hb[8 + 4 * j] - hb[0] : 0, hb[9 + 4 * j] ? hb[9 + 4 * j] - hb[0] : 0, hb[10 + 4 * j] - hb[0], hb[11 + 4 * j] - hb[0]);
+    fprintf(stderr, "\n   epi [acch_full loaded+math h_empty-ok stored] per chunk:");
+    for (int j = 0; j < 8; ++j) fprintf(stderr, " | %lld %lld %lld %lld", hb[128 + 4 * j] - hb[0], hb[129 + 4 * j] - hb[0], hb[130 + 4 * j] - hb[0], hb[131 + 4 * j] - hb[0]);
+    fprintf(stderr, "\n   final epilogue 0: acc in regs %lld | res added %lld | first barrier %lld | stats done %lld", hb[200] - hb[0], hb[201] - hb[0], hb[202] - hb[0], hb[203] - hb[0]);
+    fprintf(stderr, "\n   producer stage issue (every 4th):");
+    for (int g = 4; g < 64; g += 4) fprintf(stderr, " %lld", hb[64 + g] - hb[0]);
+    fprintf(stderr, "\n");
+  }
   return LADIFF_OK;
 }
 
@@ -545,6 +616,11 @@ int pack_weight(H* h, Arena& ar, cudaStream_t st, Weight* w, const float* W_dev,
     CK(cudaMemcpyAsync(w->bias, bias_dev, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   LAUNCH(k_pack_weight, cdiv(static_cast<long>(w->n_pad) * K, 256), 256, 0, st, W_dev, ldw, N, K, w->n_pad, w->Wt, w->pl);
+  w->swap_img = nullptr;
+  if ((N == 1024 && K == 256) || (N == 256 && K == 1024)) {   // a feed-forward matrix: also keep the k_ffn_swap streaming image
+    CK(ar.alloc(reinterpret_cast<void**>(&w->swap_img), 3ull * N * K * sizeof(op16)));
+    LAUNCH(k_pack_swap_image, cdiv(3L * 32 * 128 * 64, 256), 256, 0, st, w->pl, w->n_pad, K, N == 256 ? 1 : 0, w->swap_img);
+  }
   if (K % 64 == 0) {
     CKS(make_map(h, &w->map64, w->pl, 3ull * w->n_pad, K, K, 64));
     CKS(make_map(h, &w->map128, w->pl, 3ull * w->n_pad, K, K, 128));
@@ -732,31 +808,62 @@ int finalize_decoder(H* h, cudaStream_t st) {
   h->dec_pe = pe->dev;
   CKS(get_vec(h, P + "decoder.norm.weight", D, &h->dec_fg));
   CKS(get_vec(h, P + "decoder.norm.bias", D, &h->dec_fb));
-  std::vector<std::pair<const Raw*, const Raw*>> memproj;
+  // folded cross-attention projection of the memory latents (k_cross_ln): per layer CX_LD rows
+  //   [h * 256 + c]        kq : (W_q[h]^T W_k[h])[c, :]      bias  W_q[h]^T b_k[h]
+  //   [1024 + h * 256 + c] v' : (W_o[:, h] W_v[h])[c, :]     bias  W_o[:, h] b_v[h]
+  //   [2048 + h]           cq :  b_q[h]^T W_k[h]             bias  b_q[h] . b_k[h]
+  float *fm = nullptr, *fb = nullptr;
+  CK(cudaMalloc(&fm, static_cast<size_t>(NL) * CX_LD * D * sizeof(float)));
+  CK(cudaMalloc(&fb, static_cast<size_t>(NL) * CX_LD * sizeof(float)));
+  CK(cudaMemsetAsync(fm, 0, static_cast<size_t>(NL) * CX_LD * D * sizeof(float), st));
+  CK(cudaMemsetAsync(fb, 0, static_cast<size_t>(NL) * CX_LD * sizeof(float), st));
+  auto fold_done = [&](int s_) {
+    cudaStreamSynchronize(st);
+    cudaFree(fm);
+    cudaFree(fb);
+    return s_;
+  };
   for (int l = 0; l < NL; ++l) {
     const std::string L = P + "decoder." + block_name(l) + ".";
     DecLayerW& w = h->dec[l];
-    const Raw *ipw, *ipb, *mw, *mb;
-    CKS(get_raw(h, L + "self_attn.in_proj_weight", {3 * D, D}, &ipw));
-    CKS(get_raw(h, L + "self_attn.in_proj_bias", {3 * D}, &ipb));
-    CKS(pack_weight(h, *h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev));
-    CKS(pack_linear(h, st, &w.out, L + "self_attn.out_proj", D, D));
-    CKS(get_raw(h, L + "multihead_attn.in_proj_weight", {3 * D, D}, &mw));
-    CKS(get_raw(h, L + "multihead_attn.in_proj_bias", {3 * D}, &mb));
-    CKS(pack_weight(h, *h->warena, st, &w.q2, mw->dev, D, D, D, mb->dev));
-    memproj.push_back({mw, mb});
-    CKS(pack_linear(h, st, &w.out2, L + "multihead_attn.out_proj", D, D));
-    CKS(pack_linear(h, st, &w.ff1, L + "linear1", h->cfg.ff_size, D));
-    CKS(pack_linear(h, st, &w.ff2, L + "linear2", D, h->cfg.ff_size));
-    CKS(get_vec(h, L + "norm1.weight", D, &w.n1g));
-    CKS(get_vec(h, L + "norm1.bias", D, &w.n1b));
-    CKS(get_vec(h, L + "norm2.weight", D, &w.n2g));
-    CKS(get_vec(h, L + "norm2.bias", D, &w.n2b));
-    CKS(get_vec(h, L + "norm3.weight", D, &w.n3g));
-    CKS(get_vec(h, L + "norm3.bias", D, &w.n3b));
+    const Raw *ipw, *ipb, *mw, *mb, *ow, *ob;
+    int s_;
+    if ((s_ = get_raw(h, L + "self_attn.in_proj_weight", {3 * D, D}, &ipw)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_raw(h, L + "self_attn.in_proj_bias", {3 * D}, &ipb)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = pack_weight(h, *h->warena, st, &w.qkv, ipw->dev, D, 3 * D, D, ipb->dev)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = pack_linear(h, st, &w.out, L + "self_attn.out_proj", D, D)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_raw(h, L + "multihead_attn.in_proj_weight", {3 * D, D}, &mw)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_raw(h, L + "multihead_attn.in_proj_bias", {3 * D}, &mb)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_raw(h, L + "multihead_attn.out_proj.weight", {D, D}, &ow)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_raw(h, L + "multihead_attn.out_proj.bias", {D}, &ob)) != LADIFF_OK) return fold_done(s_);
+    w.out2_bias = ob->dev;
+    float* F = fm + static_cast<size_t>(l) * CX_LD * D;
+    float* Fb = fb + static_cast<size_t>(l) * CX_LD;
+    const float *Wq = mw->dev, *Wk = mw->dev + D * D, *Wv = mw->dev + 2 * D * D;
+    const float *bq = mb->dev, *bk = mb->dev + D, *bv = mb->dev + 2 * D;
+    for (int hd = 0; hd < 4; ++hd) {
+      const int r = hd * 64;
+      LAUNCH(k_fold_tn, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, Wq + r * D, D, Wk + r * D, D, D, 64, D, F + (hd * D) * D, D);
+      LAUNCH(k_fold_tn, 1, 256, 0, st, Wq + r * D, D, bk + r, 1, D, 64, 1, Fb + hd * D, 1);
+      LAUNCH(k_fold_matmul, cdiv(static_cast<long>(D) * D, 256), 256, 0, st, ow->dev + r, D, Wv + r * D, D, D, 64, D, F + (1024 + hd * D) * D, D);
+      LAUNCH(k_fold_matvec, 1, 256, 0, st, ow->dev + r, D, bv + r, (const float*)nullptr, D, 64, Fb + 1024 + hd * D);
+      LAUNCH(k_fold_matmul, 1, 256, 0, st, bq + r, 64, Wk + r * D, D, 1, 64, D, F + (2048 + hd) * D, D);
+      LAUNCH(k_fold_matvec, 1, 256, 0, st, bq + r, 64, bk + r, (const float*)nullptr, 1, 64, Fb + 2048 + hd);
+    }
+    if ((s_ = pack_linear(h, st, &w.ff1, L + "linear1", h->cfg.ff_size, D)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = pack_linear(h, st, &w.ff2, L + "linear2", D, h->cfg.ff_size)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_vec(h, L + "norm1.weight", D, &w.n1g)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_vec(h, L + "norm1.bias", D, &w.n1b)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_vec(h, L + "norm2.weight", D, &w.n2g)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_vec(h, L + "norm2.bias", D, &w.n2b)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_vec(h, L + "norm3.weight", D, &w.n3g)) != LADIFF_OK) return fold_done(s_);
+    if ((s_ = get_vec(h, L + "norm3.bias", D, &w.n3b)) != LADIFF_OK) return fold_done(s_);
+  }
+  {
+    int s_ = pack_weight(h, *h->warena, st, &h->memx_all, fm, D, NL * CX_LD, D, fb);
+    if (fold_done(s_) != LADIFF_OK) return s_;
   }
   for (int i = 0; i < 4; ++i) CKS(pack_linear(h, st, &h->dec_skip[i], P + "decoder.linear_blocks." + std::to_string(i), D, 2 * D));
-  CKS(pack_concat(h, st, &h->memkv_all, memproj, D, 2 * D, D));
   CKS(pack_linear(h, st, &h->dec_final, P + "final_layer", h->cfg.nfeats, D));
   h->dec_ready = true;
   // ---- encoder half of the VAE (LADiffVae.encode; only when the caller supplied its keys)
@@ -1021,6 +1128,22 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
     }
     return launch_ffn_swap(h, st, mode, f);
   }
+  if (ffn_tile_enabled(mode) && (R + 127) / 128 >= 120 && !getenv("LADIFF_NO_FFN_TILE_DEN")) {
+    // enough 128-row tiles to fill the SMs (>= 15 360 latent rows per chain): each feed-forward pair as one persistent tile kernel.
+    // Below that the separate linears win: 20 tiles (B = 256 per chain) would occupy 20 SMs for ~30 us (measured at B = 1024 in four
+    // chains: reverse loop 154 ms with tile kernels vs 115 ms with the separate linears, profiles/r02_large_batch.txt)
+    FtCall f;
+    f.X = &p->x1; f.W1 = &w.ff1; f.W2 = &w.ff2; f.M_max = R; f.M_dev = p->R; f.act = EPI_RELU; f.kind = EPI_LN;
+    f.res = p->x1.act.f32; f.ln_g = w.n2g; f.ln_b = w.n2b;
+    f.addv = p->delta + (static_cast<size_t>(l) * n + step) * S * 256; f.add_idx = p->row_seq; f.ld_add = 256;
+    f.out = p->x3.act; f.out_planes = pl;
+    CKS(launch_ffn_tile(h, st, mode, f));
+    f = FtCall();
+    f.X = &p->x3; f.W1 = &w.gff1; f.W2 = &w.gff2; f.M_max = R; f.M_dev = p->R; f.act = EPI_GELU; f.kind = EPI_LN_MOD_SILU;
+    f.ln_g = w.ffn_sn_g; f.ln_b = w.ffn_sn_b; f.mod = p->mod + static_cast<size_t>(step) * NL * 1024 + l * 1024 + 512;
+    f.out = p->sbuf.act; f.out_planes = pl;
+    return launch_ffn_tile(h, st, mode, f);
+  }
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = p->x1.act.f32;
@@ -1165,7 +1288,7 @@ struct DecodePlan {
   int *mcnt = nullptr, *moff = nullptr, *Rm = nullptr, *mrow_seq = nullptr, *mrow_t = nullptr;
   float* z = nullptr;  // staged [T,B,256]
   ActBuf zrows, x0, xa, xb, x1, x2, skip[4], a, hbuf, xn;
-  float *qkv = nullptr, *q2 = nullptr, *memkv = nullptr;
+  float *qkv = nullptr, *memx = nullptr;   // memx: folded cross-attention table [memory rows, 9 x CX_LD]
   uint64_t last_use = 0;
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
@@ -1208,8 +1331,7 @@ int build_decode_plan(H* h, DecodePlan* p, int B, int mode) {
   CKS(alloc_act(h, ar, &p->hbuf, R, 1024, f, tcm));
   CKS(alloc_act(h, ar, &p->xn, R, 256, f, tcm));
   CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * 768 * sizeof(float)));
-  CK(ar.alloc((void**)&p->q2, static_cast<size_t>(roundup(R, 128)) * 256 * sizeof(float)));
-  CK(ar.alloc((void**)&p->memkv, static_cast<size_t>(roundup(M, 128)) * NL * 512 * sizeof(float)));
+  CK(ar.alloc((void**)&p->memx, static_cast<size_t>(roundup(M, 128)) * NL * CX_LD * sizeof(float)));
   return LADIFF_OK;
 }
 
@@ -1218,8 +1340,30 @@ int enqueue_self_attention(H* h, cudaStream_t st, int mode, int pl, int B, int L
   if (mode == LADIFF_MODE_FP32 || getenv("LADIFF_ATTN_SIMT")) {
     dim3 grid((Lmax + SA_QB - 1) / SA_QB, 4, B);
     LAUNCHP(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, qkv, off, out, pl);
+  } else if (!getenv("LADIFF_ATTN_MMA_SYNC")) {
+    // tensor-core modes: (head, sequence) CTAs on tcgen05 (scores and probabilities live in tensor memory)
+    dim3 grid(4, B);
+    long long* dbg = nullptr;
+    static int dbg_left = getenv("LADIFF_AT5_DBG") ? 2 : 0;    // profiling: clock stamps of CTA (0, 0) of the first launches (needs LADIFF_NO_GRAPH=1)
+    if (dbg_left > 0) {
+      CK(cudaMalloc(&dbg, 32 * sizeof(long long)));
+      CK(cudaMemsetAsync(dbg, 0, 32 * sizeof(long long), st));
+    }
+    if (mode == LADIFF_MODE_BF16X3) LAUNCHP((k_attn_self_t5<2>), grid, At5Cfg<2>::THREADS, At5Cfg<2>::SMEM_BYTES, st, qkv, off, out, pl, dbg);
+    else LAUNCHP((k_attn_self_t5<1>), grid, At5Cfg<1>::THREADS, At5Cfg<1>::SMEM_BYTES, st, qkv, off, out, pl, dbg);
+    if (dbg) {
+      long long hb[32];
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost));
+      cudaFree(dbg);
+      --dbg_left;
+      fprintf(stderr, "  attn_t5 cta(0,0) clk:");
+      for (int i = 1; i < 32; ++i)
+        if (hb[i]) fprintf(stderr, " [%d]%lld", i, hb[i] - hb[0]);
+      fprintf(stderr, "\n");
+    }
   } else {
-    // tensor-core modes: (head, sequence) CTAs, hi/lo split products in bf16x3 mode
+    // the round-1 kernel (mma.sync fragments, scores in registers), kept for same-box A/B: LADIFF_ATTN_MMA_SYNC=1
     dim3 grid(4, B);
     const bool big = Lmax > 26 * 8;
     if (mode == LADIFF_MODE_BF16X3) {
@@ -1243,13 +1387,22 @@ int enqueue_dec_layer(H* h, DecodePlan* p, cudaStream_t st, int l, const ActBuf&
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
-  c = LinCall(); c.A = &p->x1; c.W = &w.q2; c.M_max = R; c.M_dev = p->Rf; c.out = f32_only(p->q2, 256);
-  CKS(launch_linear(h, st, mode, c));
-  LAUNCHP(k_attn_cross<8>, cdiv(static_cast<long>(R) * 32, 256), 256, 0, st, p->q2, p->memkv, NL * 512, l * 512, p->frow_seq, p->moff, p->Rf,
-         p->a.act, pl);
-  c = LinCall(); c.A = &p->a; c.W = &w.out2; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = p->x1.act.f32;
-  c.ln_g = w.n2g; c.ln_b = w.n2b; c.out = p->x2.act; c.out_planes = pl;
-  CKS(launch_linear(h, st, mode, c));
+  // cross-attention to the <= 5 latents + residual + norm2: one fp32 kernel on the folded table (no q / out-projection GEMMs)
+  {
+    dim3 grid((p->Lmax + 31) / 32, p->B);
+    if (p->T <= 5)
+      LAUNCHP(k_cross_ln<5>, grid, 256, 5 * CX_LD * sizeof(float), st, p->x1.act.f32, p->memx, NL * CX_LD, l * CX_LD, p->foff, p->moff, w.out2_bias,
+              w.n2g, w.n2b, p->x2.act, pl);
+    else
+      LAUNCHP(k_cross_ln<8>, grid, 256, 8 * CX_LD * sizeof(float), st, p->x1.act.f32, p->memx, NL * CX_LD, l * CX_LD, p->foff, p->moff, w.out2_bias,
+              w.n2g, w.n2b, p->x2.act, pl);
+  }
+  if (ffn_tile_enabled(mode)) {   // linear1 -> GELU -> linear2 -> + residual -> norm3, the 1024-wide hidden stays in tensor memory
+    FtCall f;
+    f.X = &p->x2; f.W1 = &w.ff1; f.W2 = &w.ff2; f.M_max = R; f.M_dev = p->Rf; f.act = EPI_GELU; f.kind = EPI_LN;
+    f.res = p->x2.act.f32; f.ln_g = w.n3g; f.ln_b = w.n3b; f.out = out.act; f.out_planes = pl;
+    return launch_ffn_tile(h, st, mode, f);
+  }
   c = LinCall(); c.A = &p->x2; c.W = &w.ff1; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_GELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = p->x2.act.f32;
@@ -1263,7 +1416,7 @@ int enqueue_decode_body(H* h, DecodePlan* p, cudaStream_t st) {
   const int pl = p->planes, mode = p->mode;
   LAUNCHP(k_gather_z, cdiv(static_cast<long>(p->Mmax) * 256, 256), 256, 0, st, p->z, p->moff, p->B, p->T, p->zrows.act, pl);
   LinCall c;
-  c.A = &p->zrows; c.W = &h->memkv_all; c.M_max = p->Mmax; c.M_dev = p->Rm; c.out = f32_only(p->memkv, NL * 512);
+  c.A = &p->zrows; c.W = &h->memx_all; c.M_max = p->Mmax; c.M_dev = p->Rm; c.out = f32_only(p->memx, NL * CX_LD);
   CKS(launch_linear(h, st, mode, c));
   LAUNCHP(k_dec_init, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, h->dec_pe, p->frow_t, p->Rf, p->x0.act, pl);
   const ActBuf* x = &p->x0;
@@ -1345,6 +1498,12 @@ int enqueue_enc_layer(H* h, EncodePlan* p, cudaStream_t st, int l, const ActBuf&
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
+  if (ffn_tile_enabled(mode)) {
+    FtCall f;
+    f.X = &p->x1; f.W1 = &w.ff1; f.W2 = &w.ff2; f.M_max = R; f.M_dev = p->R; f.act = EPI_GELU; f.kind = EPI_LN;
+    f.res = p->x1.act.f32; f.ln_g = w.n2g; f.ln_b = w.n2b; f.out = out.act; f.out_planes = pl;
+    return launch_ffn_tile(h, st, mode, f);
+  }
   c = LinCall(); c.A = &p->x1; c.W = &w.ff1; c.M_max = R; c.M_dev = p->R; c.epi = EPI_GELU; c.out = p->hbuf.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
   c = LinCall(); c.A = &p->hbuf; c.W = &w.ff2; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = p->x1.act.f32;
@@ -1504,6 +1663,12 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(2));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<32>(1));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_tc<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sat_smem_bytes<26>(1));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross_ln<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * CX_LD * (int)sizeof(float));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross_ln<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * CX_LD * (int)sizeof(float));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<2>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<1>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<2>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<1>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<1>::smem_bytes(48));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
@@ -1868,7 +2033,7 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
   if (!x_dev || !mod_dev || !x3_out_dev || !s_out_dev || M < 1 || layer < 0 || layer >= NL)
     return h->err.set(LADIFF_ERR_INVALID, "ladiff_ffn_test: bad argument");
   if (fused && mode == LADIFF_MODE_FP32) return h->err.set(LADIFF_ERR_INVALID, "ladiff_ffn_test: the fused kernel is a tensor-core path");
-  if (fused && ffn_swap_rt(M) == 0) fused = 0;   // above the co-resident capacity the plans run the separate linears
+  const bool tile_path = fused && ffn_swap_rt(M) == 0;   // above the co-resident capacity the plans run the persistent tile kernel per pair
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DenLayerW& w = h->den[layer];
   const int planes = mode == LADIFF_MODE_FP32 ? 0 : (mode == LADIFF_MODE_BF16X3 ? 2 : 1);
@@ -1881,6 +2046,16 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
   CKS(alloc_act(h, ar, &hb, M, 1024, !tcm, tcm));
   LAUNCHP(k_unary, cdiv(static_cast<long>(M) * 256, 256), 256, 0, st, x_dev, 256, M, 256, (int)U_COPY, x.act, planes);
   auto run = [&]() -> int {
+    if (tile_path) {
+      FtCall f;
+      f.X = &x; f.W1 = &w.ff1; f.W2 = &w.ff2; f.M_max = M; f.act = EPI_RELU; f.kind = EPI_LN; f.res = x.act.f32;
+      f.ln_g = w.n2g; f.ln_b = w.n2b; f.out = x3.act; f.out_planes = planes;
+      CKS(launch_ffn_tile(h, st, mode, f));
+      f = FtCall();
+      f.X = &x3; f.W1 = &w.gff1; f.W2 = &w.gff2; f.M_max = M; f.act = EPI_GELU; f.kind = EPI_LN_MOD_SILU;
+      f.ln_g = w.ffn_sn_g; f.ln_b = w.ffn_sn_b; f.mod = mod_dev; f.out = sb.act; f.out_planes = planes;
+      return launch_ffn_tile(h, st, mode, f);
+    }
     if (fused) {
       FfnCall f;
       f.X = &x; f.M_max = M; f.npairs = 2; f.out_planes = planes; f.res = x.act.f32;
@@ -1921,7 +2096,7 @@ int ladiff_ffn_test(ladiff_handle* h, const float* x_dev, int32_t M, int32_t lay
     *ms_per_call_host = ms / iters;
   }
   CK(cudaStreamSynchronize(st));
-  if (fused && getenv("LADIFF_DBG_STAMPS")) {
+  if (fused && !tile_path && getenv("LADIFF_DBG_STAMPS")) {
     long long* dbg = nullptr;
     const int rt = ffn_swap_rt(M);
     const int ncta = ((M + rt - 1) / rt) * 4;

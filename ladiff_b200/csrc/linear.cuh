@@ -190,7 +190,7 @@ __device__ __forceinline__ constexpr int w_plane(int pl) { return NSPLIT == 2 ? 
 //
 // Shared memory:  [ STAGES x { A planes | W planes } ]  [ per-column vectors 5 KB ]  [ mbarriers ]
 // After the last MMA retires the stage memory is dead, so the epilogue aliases its transposition tiles onto it.
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, int EW = 8>
 struct TcCfg {
   static constexpr int BM = 128, BK = 64, UMMA_K = 16;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -207,12 +207,14 @@ struct TcCfg {
   static constexpr int BAR_OFF = VEC_OFF + VEC_BYTES;
   static constexpr int STAT_BYTES = 8192;                    // LayerNorm row statistics exchanged between epilogue warps / cluster CTAs
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + STAT_BYTES + 1024 /*align slack*/;
-  static constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, each takes every other 32-column chunk
+  static constexpr int EPI_WARPS = EW;                       // EW / 4 warps per TMEM lane quarter; warp group g takes the 32-column chunks g, g + EW/4, ...
+  static constexpr int CGROUPS = EW / 4;
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int THREADS = 64 + EPI_THREADS;
   static constexpr int TILE_LD = 36;                         // floats; 144 B rows keep float4 accesses conflict-free
   static constexpr int TILE_BYTES = 32 * TILE_LD * 4;        // one warp-private 32x32 fp32 tile
-  static_assert(8 * TILE_BYTES <= STAGES * STAGE_BYTES, "epilogue tiles must fit in the dead stage memory");
+  static_assert(EW * TILE_BYTES <= STAGES * STAGE_BYTES, "epilogue tiles must fit in the dead stage memory");
+  static_assert(EW == 8 || EW == 16, "8 epilogue warps (latency-bound launches) or 16 (multi-wave launches: the epilogue is issue / latency bound)");
 };
 
 // slow path: per-thread scalar stores (scatter / unaligned / partial column chunk)
@@ -273,8 +275,8 @@ __device__ __forceinline__ void warp_load_finish(float (*tile)[36], const float4
 
 // Warp-cooperative, coalesced store of 32 finished rows x 32 cols (thread <-> row) through the warp-private tile.
 // Every store instruction writes whole 128-byte lines (fp32) / whole 32-byte sectors (bf16 planes).
-__device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs& p, long row_base, int nvalid, int col0,
-                                                int lane, const float (&y)[32]) {
+__device__ __forceinline__ void warp_store_act(float (*tile)[36], const Act& out, int out_planes, long row_base, int nvalid, int col0,
+                                               int lane, const float (&y)[32]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q)
     *reinterpret_cast<float4*>(&tile[lane][4 * q]) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
@@ -282,23 +284,23 @@ __device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs
   float4 a[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(&tile[i * 4 + (lane >> 3)][(lane & 7) * 4]);
-  const long off0 = (row_base + (lane >> 3)) * p.out.ld + col0 + (lane & 7) * 4;
-  const long step = 4L * p.out.ld;
-  if (p.out.f32) {
-    float* d = p.out.f32 + off0;
+  const long off0 = (row_base + (lane >> 3)) * out.ld + col0 + (lane & 7) * 4;
+  const long step = 4L * out.ld;
+  if (out.f32) {
+    float* d = out.f32 + off0;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (i * 4 + (lane >> 3) < nvalid) *reinterpret_cast<float4*>(d + i * step) = a[i];
   }
-  if (p.out.pl && p.out_planes > 0) {
-    op16* dh = p.out.pl + off0;
-    op16* dl = dh + static_cast<long>(p.out.rows_alloc) * p.out.ld;
-    const bool two = p.out_planes > 1;
+  if (out.pl && out_planes > 0) {
+    op16* dh = out.pl + off0;
+    op16* dl = dh + static_cast<long>(out.rows_alloc) * out.ld;
+    const bool two = out_planes > 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       uint32_t h01, l01, h23, l23;
-      split2_op(a[i].x, a[i].y, p.out_planes, h01, l01);
-      split2_op(a[i].z, a[i].w, p.out_planes, h23, l23);
+      split2_op(a[i].x, a[i].y, out_planes, h01, l01);
+      split2_op(a[i].z, a[i].w, out_planes, h23, l23);
       if (i * 4 + (lane >> 3) < nvalid) {
         *reinterpret_cast<uint2*>(dh + i * step) = make_uint2(h01, h23);
         if (two) *reinterpret_cast<uint2*>(dl + i * step) = make_uint2(l01, l23);
@@ -307,12 +309,16 @@ __device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs
   }
   __syncwarp();
 }
+__device__ __forceinline__ void warp_store_rows(float (*tile)[36], const LinArgs& p, long row_base, int nvalid, int col0,
+                                                int lane, const float (&y)[32]) {
+  warp_store_act(tile, p.out, p.out_planes, row_base, nvalid, col0, lane, y);
+}
 
-template <int BN, int NSPLIT, int EPI>
-__global__ void __launch_bounds__(TcCfg<BN, NSPLIT>::THREADS, TcCfg<BN, NSPLIT>::MIN_CTAS)
+template <int BN, int NSPLIT, int EPI, int EW = 8>
+__global__ void __launch_bounds__(TcCfg<BN, NSPLIT, EW>::THREADS, TcCfg<BN, NSPLIT, EW>::MIN_CTAS)
 k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW, const LinArgs p) {
-  using C = TcCfg<BN, NSPLIT>;
+  using C = TcCfg<BN, NSPLIT, EW>;
   constexpr int STAGES = C::STAGES;
   constexpr bool LN = (EPI == EPI_LN || EPI == EPI_LN_MOD_SILU);
   const int M = p.M_dev ? min(p.M_max, *p.M_dev) : p.M_max;
@@ -448,8 +454,8 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     __syncwarp();
   } else {
-    // ===== epilogue: 8 warps; thread <-> accumulator row, warp pair (w, w+4) shares a TMEM lane quarter and splits
-    // the 32-column chunks between them (chunk c belongs to half c & 1) =====
+    // ===== epilogue: EW warps; thread <-> accumulator row, the EW / 4 warps of a TMEM lane quarter split the 32-column chunks
+    // between them (chunk c belongs to column group c % (EW / 4)) =====
     // (1) while the mainloop runs: per-column vectors -> shared memory (read back as broadcast float4)
     const int et = threadIdx.x - 64;
     for (int i = et; i < BN; i += C::EPI_THREADS) vec[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
@@ -466,17 +472,18 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         vec[1024 + i] = p.mod[256 + i];
       }
     }
-    const int ew = warp - 2;  // 0..7
+    constexpr int CG = C::CGROUPS;
+    const int ew = warp - 2;  // 0..EW-1
     const int wq = warp & 3;  // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
-    const int ch = ew >> 2;   // column half
+    const int ch = ew >> 2;   // column group
     const int r = wq * 32 + lane;
     const long row = static_cast<long>(tile_m) * C::BM + r;
     const bool valid = row < M;
     const long row_base = static_cast<long>(tile_m) * C::BM + wq * 32;
     const int nvalid = static_cast<int>(min(32L, static_cast<long>(M) - row_base));  // may be <= 0
     const long drow = (valid && p.row_map) ? p.row_map[row] : row;
-    float* xs = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);  // [2 passes][2 halves][128 rows] LayerNorm partials
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    float* xs = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);  // [2 passes][CG column groups][128 rows] LayerNorm partials
+    asm volatile("bar.sync 1, %0;" ::"n"(C::EPI_THREADS) : "memory");  // the epilogue warps only
     // residual of the first LayerNorm chunk: requested while the mainloop runs
     float4 rpre[8];
     const bool ln_res = LN && EPI == EPI_LN && p.res != nullptr;
@@ -495,10 +502,10 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // partial sums exchanged through shared memory.
       float s = 0.f;
 #pragma unroll 1
-      for (int c = ch; c < BN / 32; c += 2) {
+      for (int c = ch; c < BN / 32; c += CG) {
         if (ln_res) {
           warp_load_finish(tile, rpre, lane, t);
-          if (c + 2 < BN / 32) warp_load_issue(rpre, p.res, p.ldres, row_base, nvalid, (c + 2) * 32, lane);   // next chunk in flight
+          if (c + CG < BN / 32) warp_load_issue(rpre, p.res, p.ldres, row_base, nvalid, (c + CG) * 32, lane);   // next chunk in flight
         }
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
@@ -515,12 +522,15 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc::tmem_st32(trow + c * 32, v);
       }
       xs[ch * 128 + r] = s;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mean = (xs[r] + xs[128 + r]) * (1.f / 256.f);
+      asm volatile("bar.sync 1, %0;" ::"n"(C::EPI_THREADS) : "memory");
+      float msum = 0.f;
+#pragma unroll
+      for (int k = 0; k < CG; ++k) msum += xs[k * 128 + r];
+      const float mean = msum * (1.f / 256.f);
       if (threadIdx.x == 64) STAMP(10);
       float q2 = 0.f;
 #pragma unroll 1
-      for (int c = ch; c < BN / 32; c += 2) {
+      for (int c = ch; c < BN / 32; c += CG) {
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -528,12 +538,15 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           q2 += d * d;
         }
       }
-      xs[256 + ch * 128 + r] = q2;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float rstd = 1.0f / sqrtf((xs[256 + r] + xs[384 + r]) * (1.f / 256.f) + LD_EPS);
+      xs[(CG + ch) * 128 + r] = q2;
+      asm volatile("bar.sync 1, %0;" ::"n"(C::EPI_THREADS) : "memory");
+      float qsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < CG; ++k) qsum += xs[(CG + k) * 128 + r];
+      const float rstd = 1.0f / sqrtf(qsum * (1.f / 256.f) + LD_EPS);
       if (threadIdx.x == 64) STAMP(11);
 #pragma unroll 1
-      for (int c = ch; c < BN / 32; c += 2) {
+      for (int c = ch; c < BN / 32; c += CG) {
         if (EPI == EPI_LN && p.addv) warp_load_rows(tile, p.addv, p.ld_add, p.add_idx, row_base, nvalid, c * 32, lane, t);
         tc::tmem_ld32(trow + c * 32, v);
 #pragma unroll
@@ -564,7 +577,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     } else {
 #pragma unroll 1
-      for (int c = ch; c < BN / 32; c += 2) {
+      for (int c = ch; c < BN / 32; c += CG) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.n_store) break;  // warp-uniform
         const bool full_chunk = fast && (col0 + 32 <= p.n_store);

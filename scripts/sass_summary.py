@@ -26,7 +26,7 @@ for line in out.split("\n"):
     m = re.search(r"arch = (sm_\w+)", line)
     if m:
         arch.add(m.group(1))
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m and cur:
         n_ins += 1
         op = m.group(1).split(".")[0]

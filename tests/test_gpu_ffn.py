@@ -43,6 +43,26 @@ def test_ffn_fused(engine, oracle_sd, mode, M, layer):
         assert err < TOL[mode], f"{mode} M={M} layer={layer} {name}: rel max err {err:.3e}"
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,layer", [(1777, 1), (4173, 6), (25088, 3)])
+def test_ffn_tile(engine, oracle_sd, mode, M, layer):
+    """Above 1776 rows every feed-forward pair runs as ONE persistent tile kernel (csrc/ffn_tile.cuh: hidden activation kept in
+    tensor memory as the A operand of the second GEMM): both epilogue kinds (ReLU + LN + residual; GELU + LN * mod + SiLU),
+    a ragged last tile, one and two tiles per CTA (25 088 rows = 196 tiles on 148 SMs)."""
+    from ladiff_b200._lib import MODES
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + layer)
+    x = torch.randn((M, 256), generator=g)
+    mod = 0.3 * torch.randn((512,), generator=g)
+    x3r, sr = ref_ffn(oracle_sd, layer, x, mod)
+    x3, s, _ = engine.ffn_test(x.cuda(), layer, mod.cuda(), mode=MODES[mode], fused=True)
+    assert torch.isfinite(x3).all() and torch.isfinite(s).all()
+    for name, got, ref in (("x3", x3, x3r), ("s", s, sr)):
+        err = (got.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < TOL[mode], f"{mode} M={M} layer={layer} {name}: rel max err {err:.3e}"
+    x3b, sb, _ = engine.ffn_test(x.cuda(), layer, mod.cuda(), mode=MODES[mode], fused=True)
+    assert torch.equal(x3, x3b) and torch.equal(s, sb)
+
+
 def test_ffn_fused_deterministic(engine):
     from ladiff_b200._lib import MODES
     g = torch.Generator(device="cpu").manual_seed(5)

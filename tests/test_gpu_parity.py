@@ -10,8 +10,11 @@ from oracle import ladiff_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-# max-abs tolerance on decoded features (north_star: 1e-3 on the fp32-accumulate paths; bf16 measured)
-FEATS_TOL = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 0.25}
+# max-abs tolerance on decoded features.  fp32 / x3 ("bf16x3" in the API: fp16 hi/lo split operands, 3 products): the 1e-3 contract of
+# north_star.  bf16: 2 x the largest error MEASURED on the stated configurations (B = 128 x 196 frames: 0.139; ragged: 0.144;
+# KIT B = 256: 0.147 -- the `[bf16 measured]` lines of this file, also printed live by bench.py as parity.bf16_max_abs_err) on
+# features with abs-max 2.5 - 4.4: single-pass bf16 operands (8 mantissa bits) under the ~100x amplification of the 50-step CFG loop.
+FEATS_TOL = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 0.30}
 
 
 def ddim_tables(n):
@@ -69,7 +72,8 @@ def test_sampling_vs_reference(engine, golden_dir, mode):
     ts, c1, c2 = ddim_tables(20)
     z20 = engine.diffusion_reverse(text.cuda(), lengths, noise.cuda(), ts, c1, c2, 7.5, MODES[mode]).cpu()
     e20 = (z20 - torch.from_numpy(G["z20"])).abs().max().item()
-    assert e20 < {"fp32": 5e-3, "bf16x3": 5e-2, "bf16": 50.0}[mode], f"{mode}: 20-step latents err {e20:.3e}"
+    print(f"[{mode}] 20-step latents max-abs err {e20:.3e} (scale {torch.from_numpy(G['z20']).abs().max():.1f})")
+    assert e20 < {"fp32": 5e-3, "bf16x3": 2e-2, "bf16": 50.0}[mode], f"{mode}: 20-step latents err {e20:.3e}"
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
