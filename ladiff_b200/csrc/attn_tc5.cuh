@@ -27,6 +27,7 @@ struct At5Cfg {
   static constexpr int V_BYTES = (AT5_MAXL / 64) * 64 * 128;  // V^T: key blocks of 64 x [64 head dims x 128 B] (per plane)
   static constexpr int RED_BYTES = 2 * 2 * 128 * 4;         // [max | sum][column half][128 rows] softmax partials
   static constexpr int SMEM_BYTES = NSPLIT * (Q_BYTES + K_BYTES + V_BYTES) + RED_BYTES + 64 + 1024 /*alignment slack*/;
+  static_assert(V_BYTES == K_BYTES, "the TMA staging path stores V like K: [keys x 128 B]");
   // tensor memory columns: S [0, 256) fp32 | P hi [256, 384) | P lo [384, 512) | O [0, 64) over the (by then dead) scores
   static constexpr int TMEM_COLS = 512, COL_O = 0, COL_PHI = 256, COL_PLO = 384;
 };
@@ -86,9 +87,16 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int L,
 }
 }  // namespace at5
 
-template <int NSPLIT>
+// TMAQ = true: q | k | v arrive as 16-bit operand planes written by the in-projection GEMM's epilogue ([planes][rows_alloc][768], the
+// tensor map of that buffer has boxes of 128 rows x 64 columns = one head of 128 rows): the three operands of the (sequence, head) are
+// pulled by a dozen TMA boxes straight into their swizzled tiles -- no fp32 read, no conversion, no transposition (V is consumed
+// as an MN-major B operand: row = key, 128 bytes = the 64 head dims), and the 1/8 of the scores moves into the softmax exponent.
+// Rows behind the sequence inside a box belong to the next sequence or to the zero-initialised padding of the buffer: finite values,
+// whose keys get probability 0.  TMAQ = false: the fp32 staging path (q k v as one fp32 [rows, 768] buffer).
+template <int NSPLIT, bool TMAQ>
 __global__ void __launch_bounds__(At5Cfg<NSPLIT>::THREADS, 1)
-k_attn_self_t5(const float* __restrict__ qkv, const int* __restrict__ foff, Act out, int planes, long long* dbg) {
+k_attn_self_t5(const __grid_constant__ CUtensorMap tmQKV, int plane_rows, const float* __restrict__ qkv, const int* __restrict__ foff,
+               Act out, int planes, long long* dbg) {
   using C = At5Cfg<NSPLIT>;
 #define ASTAMP(i) do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) dbg[i] = clock64(); } while (0)
   ASTAMP(0);
@@ -105,21 +113,38 @@ k_attn_self_t5(const float* __restrict__ qkv, const int* __restrict__ foff, Act 
   uint8_t* Vt = Ks + NSPLIT * C::K_BYTES;          // [plane][key block][64 x 128 B]
   float* red = reinterpret_cast<float*>(Vt + NSPLIT * C::V_BYTES);   // [max | sum][half][128]
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * 2 * 128);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar_ld = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NW = C::THREADS / 32;
 
   if (warp == 0) {
     if (lane == 0) {
       tc::mbar_init(bar, 1);
+      tc::mbar_init(bar_ld, 1);
       tc::fence_barrier_init();
+      tc::fence_proxy_async();
+      if (TMAQ) {
+        // all operand boxes of this (sequence, head) on one barrier; a box always delivers its full 16 KB (rows past the tensor are zero-filled)
+        const int nqt_ = (L + 127) >> 7, nkt_ = (Lp + 127) >> 7;
+        tc::mbar_expect_tx(bar_ld, static_cast<uint32_t>(NSPLIT * (nqt_ + 2 * nkt_) * 16384));
+        for (int pl = 0; pl < NSPLIT; ++pl) {
+          const int prow = pl * plane_rows + r0;
+          for (int t = 0; t < nqt_; ++t) tc::tma_load_2d(Qs + pl * C::Q_BYTES + t * 16384, &tmQKV, bar_ld, h * 64, prow + t * 128);
+          for (int t = 0; t < nkt_; ++t) {
+            tc::tma_load_2d(Ks + pl * C::K_BYTES + t * 16384, &tmQKV, bar_ld, 256 + h * 64, prow + t * 128);
+            tc::tma_load_2d(Vt + pl * C::V_BYTES + t * 16384, &tmQKV, bar_ld, 512 + h * 64, prow + t * 128);
+          }
+        }
+      }
     }
     __syncwarp();
     tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc::tmem_relinquish();
   }
-  // ---- operand staging: q (pre-scaled by 1/8, exact) and k as row-major tiles, v transposed.  Rows >= L are zero.
   const int nqt = (L + 127) >> 7;                  // query tiles
+  if (!TMAQ) {
+  // ---- operand staging: q (pre-scaled by 1/8, exact) and k as row-major tiles, v transposed.  Rows >= L are zero.
   const float* base = qkv + static_cast<long>(r0) * 768 + h * 64;
   // (256 query rows + 256 key rows) x 16 float4 / 256 threads = 16 + 16 per thread, all in flight at once
   at5::stage_rows<NSPLIT, 16>(base, L, nqt * 128, 0.125f, Qs, C::Q_BYTES, tid, C::THREADS);
@@ -157,6 +182,10 @@ k_attn_self_t5(const float* __restrict__ qkv, const int* __restrict__ foff, Act 
       }
     }
   }
+  } else {
+    __syncthreads();                // the barrier was initialised (and the loads issued) by one lane of warp 0
+    tc::mbar_wait(bar_ld, 0);
+  }
   ASTAMP(2);
   tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc::tc_fence_before();
@@ -165,11 +194,12 @@ k_attn_self_t5(const float* __restrict__ qkv, const int* __restrict__ foff, Act 
   ASTAMP(3);
   const uint32_t tmem = *tmem_slot;
   const uint32_t qs_u = tc::smem_u32(Qs), ks_u = tc::smem_u32(Ks), vt_u = tc::smem_u32(Vt);
-  const uint32_t idesc_s = tc::idesc_op<NSPLIT>(128, Lp), idesc_o = tc::idesc_op<NSPLIT>(128, 64);
+  // TMAQ: V tiles are [key][64 head dims] = an MN-major B operand (instruction descriptor bit 16), 8-key groups 1024 B apart
+  const uint32_t idesc_s = tc::idesc_op<NSPLIT>(128, Lp), idesc_o = tc::idesc_op<NSPLIT>(128, 64) | (TMAQ ? (1u << 16) : 0u);
   const int wq = warp & 3, half = warp >> 2;                          // TMEM lane quarter / column half of this warp
   const int row = wq * 32 + lane;                                     // query row inside the tile
   const uint32_t tlane = static_cast<uint32_t>(wq * 32) << 16;
-  const float LOG2E = 1.4426950408889634f;
+  const float LOG2E = TMAQ ? 0.125f * 1.4426950408889634f : 1.4426950408889634f;   // TMAQ: q is not pre-scaled, 1/sqrt(64) goes here
   const int nch = (Lp + 31) >> 5;
   uint32_t phase = 0;
 
@@ -240,7 +270,7 @@ k_attn_self_t5(const float* __restrict__ qkv, const int* __restrict__ foff, Act 
       if (tc::elect_one()) {
         const int nks = Lp >> 4;
         for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t vo = (ks >> 2) * 8192 + (ks & 3) * 32;
+          const uint32_t vo = TMAQ ? ks * 2048 : (ks >> 2) * 8192 + (ks & 3) * 32;
           const uint64_t v_hi = tc::smem_desc_sw128(vt_u + vo);
           const uint32_t p_hi = tmem + C::COL_PHI + ks * 8;
           if (NSPLIT == 1) {

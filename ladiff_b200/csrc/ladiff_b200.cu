@@ -1287,7 +1287,7 @@ struct DecodePlan {
   int *cnt = nullptr, *foff = nullptr, *Rf = nullptr, *frow_seq = nullptr, *frow_t = nullptr, *frow_dst = nullptr;
   int *mcnt = nullptr, *moff = nullptr, *Rm = nullptr, *mrow_seq = nullptr, *mrow_t = nullptr;
   float* z = nullptr;  // staged [T,B,256]
-  ActBuf zrows, x0, xa, xb, x1, x2, skip[4], a, hbuf, xn;
+  ActBuf zrows, x0, xa, xb, x1, x2, skip[4], a, hbuf, xn, qkvp;   // qkvp: q | k | v operand planes of the self-attention (tensor-core modes)
   float *qkv = nullptr, *memx = nullptr;   // memx: folded cross-attention table [memory rows, 9 x CX_LD]
   uint64_t last_use = 0;
   cudaGraphExec_t exec = nullptr;
@@ -1331,12 +1331,17 @@ int build_decode_plan(H* h, DecodePlan* p, int B, int mode) {
   CKS(alloc_act(h, ar, &p->hbuf, R, 1024, f, tcm));
   CKS(alloc_act(h, ar, &p->xn, R, 256, f, tcm));
   CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * 768 * sizeof(float)));
+  if (tcm) CKS(alloc_act(h, ar, &p->qkvp, R, 768, false, true));
   CK(ar.alloc((void**)&p->memx, static_cast<size_t>(roundup(M, 128)) * NL * CX_LD * sizeof(float)));
   return LADIFF_OK;
 }
 
 // ragged self-attention of B sequences of at most Lmax rows (qkv [rows, 768], off[B + 1]) -> out [rows, 256]
-int enqueue_self_attention(H* h, cudaStream_t st, int mode, int pl, int B, int Lmax, const float* qkv, const int* off, const Act& out) {
+// tensor-core modes: the in-projection writes q | k | v as 16-bit operand planes (qkvp) and the attention kernel pulls them by TMA
+bool attn_planes_input(int mode) {
+  return mode != LADIFF_MODE_FP32 && !getenv("LADIFF_ATTN_SIMT") && !getenv("LADIFF_ATTN_MMA_SYNC") && !getenv("LADIFF_ATTN_F32_STAGE");
+}
+int enqueue_self_attention(H* h, cudaStream_t st, int mode, int pl, int B, int Lmax, const float* qkv, const ActBuf* qkvp, const int* off, const Act& out) {
   if (mode == LADIFF_MODE_FP32 || getenv("LADIFF_ATTN_SIMT")) {
     dim3 grid((Lmax + SA_QB - 1) / SA_QB, 4, B);
     LAUNCHP(k_attn_self, grid, 256, sizeof(SelfAttnSmem), st, qkv, off, out, pl);
@@ -1349,8 +1354,16 @@ int enqueue_self_attention(H* h, cudaStream_t st, int mode, int pl, int B, int L
       CK(cudaMalloc(&dbg, 32 * sizeof(long long)));
       CK(cudaMemsetAsync(dbg, 0, 32 * sizeof(long long), st));
     }
-    if (mode == LADIFF_MODE_BF16X3) LAUNCHP((k_attn_self_t5<2>), grid, At5Cfg<2>::THREADS, At5Cfg<2>::SMEM_BYTES, st, qkv, off, out, pl, dbg);
-    else LAUNCHP((k_attn_self_t5<1>), grid, At5Cfg<1>::THREADS, At5Cfg<1>::SMEM_BYTES, st, qkv, off, out, pl, dbg);
+    if (attn_planes_input(mode)) {
+      if (!qkvp || !qkvp->has_map) return h->err.set(LADIFF_ERR_STATE, "self-attention: the q | k | v operand planes are missing");
+      const int prow = qkvp->act.rows_alloc;
+      if (mode == LADIFF_MODE_BF16X3) LAUNCHP((k_attn_self_t5<2, true>), grid, At5Cfg<2>::THREADS, At5Cfg<2>::SMEM_BYTES, st, qkvp->map, prow, qkv, off, out, pl, dbg);
+      else LAUNCHP((k_attn_self_t5<1, true>), grid, At5Cfg<1>::THREADS, At5Cfg<1>::SMEM_BYTES, st, qkvp->map, prow, qkv, off, out, pl, dbg);
+    } else {
+      const CUtensorMap dummy{};
+      if (mode == LADIFF_MODE_BF16X3) LAUNCHP((k_attn_self_t5<2, false>), grid, At5Cfg<2>::THREADS, At5Cfg<2>::SMEM_BYTES, st, dummy, 0, qkv, off, out, pl, dbg);
+      else LAUNCHP((k_attn_self_t5<1, false>), grid, At5Cfg<1>::THREADS, At5Cfg<1>::SMEM_BYTES, st, dummy, 0, qkv, off, out, pl, dbg);
+    }
     if (dbg) {
       long long hb[32];
       CK(cudaStreamSynchronize(st));
@@ -1382,8 +1395,9 @@ int enqueue_dec_layer(H* h, DecodePlan* p, cudaStream_t st, int l, const ActBuf&
   const int mode = p->mode, pl = p->planes, R = p->Rmax;
   LinCall c;
   c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->Rf; c.out = f32_only(p->qkv, 768);
+  if (attn_planes_input(mode)) { c.out = Act{nullptr, p->qkvp.act.pl, 768, p->qkvp.act.rows_alloc}; c.out_planes = pl; }
   CKS(launch_linear(h, st, mode, c));
-  CKS(enqueue_self_attention(h, st, mode, pl, p->B, p->Lmax, p->qkv, p->foff, p->a.act));
+  CKS(enqueue_self_attention(h, st, mode, pl, p->B, p->Lmax, p->qkv, &p->qkvp, p->foff, p->a.act));
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->Rf; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
@@ -1444,7 +1458,7 @@ struct EncodePlan {
   int B = 0, mode = 0, T = 0, Lmax = 0, Rmax = 0, Fmax = 0, planes = 0;
   int *cnt = nullptr, *off = nullptr, *R = nullptr, *row_seq = nullptr, *row_t = nullptr;
   int *fcnt = nullptr, *foff = nullptr, *Rf = nullptr, *frow_seq = nullptr, *frow_t = nullptr, *mcnt = nullptr;
-  ActBuf feats, x0, xa, xb, x1, skip[4], a, hbuf;
+  ActBuf feats, x0, xa, xb, x1, skip[4], a, hbuf, qkvp;
   float *emb = nullptr, *qkv = nullptr, *xn = nullptr;
   uint64_t last_use = 0;
 };
@@ -1481,11 +1495,13 @@ int build_encode_plan(H* h, EncodePlan* p, int B, int mode) {
   CKS(alloc_act(h, ar, &p->a, R, 256, f, tcm));
   CKS(alloc_act(h, ar, &p->hbuf, R, 1024, f, tcm));
   CK(ar.alloc((void**)&p->qkv, static_cast<size_t>(roundup(R, 128)) * 768 * sizeof(float)));
+  if (tcm) CKS(alloc_act(h, ar, &p->qkvp, R, 768, false, true));
   CK(ar.alloc((void**)&p->xn, static_cast<size_t>(roundup(R, 128)) * 256 * sizeof(float)));
   return LADIFF_OK;
 }
 
-int enqueue_self_attention(H* h, cudaStream_t st, int mode, int planes, int B, int Lmax, const float* qkv, const int* off, const Act& out);
+int enqueue_self_attention(H* h, cudaStream_t st, int mode, int planes, int B, int Lmax, const float* qkv, const ActBuf* qkvp, const int* off, const Act& out);
+bool attn_planes_input(int mode);
 
 // TransformerEncoderLayer.forward_post (operator/cross_attention.py:293-307, gelu): self-attention -> +res -> LN -> FFN -> +res -> LN
 int enqueue_enc_layer(H* h, EncodePlan* p, cudaStream_t st, int l, const ActBuf& in, const ActBuf& out) {
@@ -1493,8 +1509,9 @@ int enqueue_enc_layer(H* h, EncodePlan* p, cudaStream_t st, int l, const ActBuf&
   const int mode = p->mode, pl = p->planes, R = p->Rmax;
   LinCall c;
   c.A = &in; c.W = &w.qkv; c.M_max = R; c.M_dev = p->R; c.out = f32_only(p->qkv, 768);
+  if (attn_planes_input(mode)) { c.out = Act{nullptr, p->qkvp.act.pl, 768, p->qkvp.act.rows_alloc}; c.out_planes = pl; }
   CKS(launch_linear(h, st, mode, c));
-  CKS(enqueue_self_attention(h, st, mode, pl, p->B, p->Lmax, p->qkv, p->off, p->a.act));
+  CKS(enqueue_self_attention(h, st, mode, pl, p->B, p->Lmax, p->qkv, &p->qkvp, p->off, p->a.act));
   c = LinCall(); c.A = &p->a; c.W = &w.out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_LN; c.res = in.act.f32;
   c.ln_g = w.n1g; c.ln_b = w.n1b; c.out = p->x1.act; c.out_planes = pl;
   CKS(launch_linear(h, st, mode, c));
@@ -1667,8 +1684,10 @@ int ladiff_create(const ladiff_config* cfg, ladiff_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross_ln<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * CX_LD * (int)sizeof(float));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<2>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<1>::SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<2>::SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<1>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<2>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<2>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<1>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_self_t5<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, At5Cfg<1>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<1>::smem_bytes(48));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ffn_swap<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SwapCfg<2>::smem_bytes(48));
