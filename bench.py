@@ -431,7 +431,7 @@ def run_own(args):
             tf = 2.0 * M * N * K_ / (ms / 1e3) / 1e12
             kern[name] = {"M": M, "N": N, "K": K_, "us": ms * 1e3, "tflops": tf, "frac_of_bf16_burst": tf / peaks["bf16_burst"]}
         extra["kernels"] = kern
-        # the dominant kernel of the step (43 % of the launch-list time, profiles/r01i_launches_bf16x3.summary.txt): the fused
+        # the dominant kernel of the step (43 % of the launch-list time, profiles/r02b_launches.summary.txt): the fused
         # feed-forward pairs of one denoiser layer (k_ffn_swap), timed alone with CUDA events inside the library on its stream
         xk = torch.randn((2 * B * 5, 256), generator=g).to(dev)
         mk = (0.3 * torch.randn((512,), generator=g)).to(dev)
@@ -558,7 +558,7 @@ def run_own(args):
             "note": ("algorithmic FLOPs per launch = 1280 rows x 4 x lin(256,1024) (the two feed-forward pairs of one denoiser layer, "
                      "SURVEY.md 8d rows 'sa ReLU-FFN' + 'GELU FFN'); bf16x3 issues 3x these on the tensor pipe; duration = CUDA events "
                      f"around 200 back-to-back launches; peak = bf16 burst of {peaks['source']}; traffic = dram read+write per launch "
-                     "of the ncu --set full capture in profiles/r01h_ncu_full_layer_kernels.txt"),
+                     "of the ncu --set full capture in profiles/r02b_ncu_full_kernels.txt"),
             "path": path}
     out.update(extra)
     emit(json.dumps(out))
