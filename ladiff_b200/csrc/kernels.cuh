@@ -232,15 +232,16 @@ __global__ void __launch_bounds__(256 * SEQS, SEQS == 1 ? 2 : 1) k_attn_ln(const
                                                  unsigned long long* trace) {
   if (trace && threadIdx.x == 0) atomicMin(trace, ktimer());
   constexpr int NK = MAXT + 2;
-  __shared__ float Qs_[SEQS][MAXT][256];
-  __shared__ float Ks_[SEQS][NK][256];
-  __shared__ float Ps_[SEQS][MAXT][4][NK];
-  __shared__ float red_[SEQS][2][8][MAXT];
+  constexpr int G = NK <= 8 ? 8 : 16;   // lanes per (row, head) group of the score phase = padded key count of a probability row
+  __shared__ __align__(16) float Qs_[SEQS][MAXT][256];
+  __shared__ __align__(16) float Ks_[SEQS][NK][256];
+  __shared__ __align__(16) float Ps_[SEQS][MAXT][4][G];
+  __shared__ __align__(16) float red_[SEQS][2][MAXT][8];   // [sum | M2][row][warp]
   const int half = SEQS > 1 ? threadIdx.x >> 8 : 0, tid = threadIdx.x & 255;
   float (*Qs)[256] = Qs_[half];
   float (*Ks)[256] = Ks_[half];
-  float (*Ps)[4][NK] = Ps_[half];
-  float (*red)[8][MAXT] = red_[half];
+  float (*Ps)[4][G] = Ps_[half];
+  float (*red)[MAXT][8] = red_[half];
   const int s = blockIdx.x * SEQS + half;
   // the row offsets and the per-column vectors are written once per call, long before the previous grid: load them BEFORE the
   // dependency wait (a dependent global round trip costs ~1.8 us on the critical path of every layer otherwise)
@@ -276,8 +277,178 @@ __global__ void __launch_bounds__(256 * SEQS, SEQS == 1 ? 2 : 1) k_attn_ln(const
   }
   asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
   if (trace && tid == 0) atomicMin(trace + 2, ~ktimer());
-  // ---- scores: element e = (i, h, j); the 64-dim dot product walks d rotated by the lane to avoid bank conflicts
-  for (int e = tid; e < m * 4 * NK; e += 256) {
+  // ---- scores + softmax in one phase.  The compute part of this kernel is bound by shared-memory INSTRUCTIONS, not by math (a
+  // scalar broadcast load per FMA): so the 64-long dot products read q and k as float4 (16-byte chunks rotated by the lane: the 8
+  // lanes of a quarter-warp phase hit 32 distinct banks), the G lanes of a group hold the keys of one (row, head) and do the
+  // softmax with shuffles (no shared-memory round trip, no single-warp serial pass), and the probabilities are stored as padded
+  // rows of G floats that the output phase reads back as float4.
+  for (int t = tid; t < MAXT * 4 * G; t += 256) {      // warp-uniform trip count (multiples of 32)
+    const int j = t % G, ih = t / G, h = ih & 3, i = ih >> 2;
+    const bool on = i < m && j < NK && (j < m || j >= MAXT);
+    float sc = -INFINITY;
+    if (on) {
+      const float4* qp = reinterpret_cast<const float4*>(&Qs[i][h * 64]);
+      const float4* kp = reinterpret_cast<const float4*>(&Ks[j][h * 64]);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const int dd = (d + lane) & 15;
+        const float4 q4 = qp[dd], k4 = kp[dd];
+        a0 = fmaf(q4.x, k4.x, a0);
+        a1 = fmaf(q4.y, k4.y, a1);
+        a2 = fmaf(q4.z, k4.z, a2);
+        a3 = fmaf(q4.w, k4.w, a3);
+      }
+      sc = (a0 + a1) + (a2 + a3);
+    }
+    float mx = sc;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float pe = on ? expf(sc - mx) : 0.f;       // rows >= m: every lane off -> probabilities 0
+    float den = pe;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+    Ps[i][h][j] = den > 0.f ? pe / den : 0.f;
+  }
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  if (trace && tid == 0) atomicMin(trace + 5, ~ktimer());
+  // ---- out[i, c] = sum_h sum_j P[i][h][j] v'[h][j][c]  + out_proj bias + residual
+  float acc[MAXT];
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i) acc[i] = boc + xr[i];
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i)
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float pr[G];
+#pragma unroll
+      for (int q = 0; q < G / 4; ++q) {
+        const float4 p4 = *reinterpret_cast<const float4*>(&Ps[i][h][4 * q]);   // broadcast float4: G / 4 loads per (row, head)
+        pr[4 * q] = p4.x; pr[4 * q + 1] = p4.y; pr[4 * q + 2] = p4.z; pr[4 * q + 3] = p4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < NK; ++j) acc[i] = fmaf(pr[j], v[h][j], acc[i]);        // rows >= m: P == 0
+    }
+  if (trace && tid == 0) atomicMin(trace + 6, ~ktimer());
+  // ---- LayerNorm over the 256 columns (one per thread), exact two-pass variance with ONE CTA barrier: every warp reduces its
+  // 32 columns about its own mean, the 8 (sum, M2) pairs are combined with the parallel-variance formula
+  //   M2 = sum_w M2_w + 32 sum_w (mean_w - mean)^2
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i) {
+    const float s1 = warp_sum(i < m ? acc[i] : 0.f);
+    const float d = acc[i] - s1 * (1.f / 32.f);
+    const float s2 = warp_sum(i < m ? d * d : 0.f);
+    if (lane == 0) {
+      red[0][i][warp] = s1;
+      red[1][i][warp] = s2;
+    }
+  }
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  if (trace && tid == 0) atomicMin(trace + 7, ~ktimer());
+  // normalised rows (and the layer input, when it is kept) go through the dead q / k tiles so that the global stores below are
+  // 16 bytes (fp32) / 8 bytes (a plane) per thread instead of one 4- / 2-byte element: 4x fewer store instructions
+  const bool keep_x = xcopy.f32 || xcopy.pl;
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i) {
+    if (i < m) {
+      const float4 sa = *reinterpret_cast<const float4*>(&red[0][i][0]), sb = *reinterpret_cast<const float4*>(&red[0][i][4]);
+      const float4 qa = *reinterpret_cast<const float4*>(&red[1][i][0]), qb = *reinterpret_cast<const float4*>(&red[1][i][4]);
+      const float mean = ((sa.x + sa.y) + (sa.z + sa.w) + (sb.x + sb.y) + (sb.z + sb.w)) * (1.f / 256.f);
+      const float sw[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+      float m2 = (qa.x + qa.y) + (qa.z + qa.w) + (qb.x + qb.y) + (qb.z + qb.w);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float dm = sw[w] * (1.f / 32.f) - mean;
+        m2 = fmaf(32.f * dm, dm, m2);
+      }
+      const float rstd = 1.0f / sqrtf(m2 * (1.f / 256.f) + LD_EPS);
+      Qs[i][c] = (acc[i] - mean) * rstd * gc + bc;
+      if (keep_x) Ks[i][c] = xr[i];
+    }
+  }
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  for (int idx = tid; idx < m * 64; idx += 256) {
+    const int i = idx >> 6, c4 = (idx & 63) * 4;
+    const long row = r0 + i;
+    const float4 y = *reinterpret_cast<const float4*>(&Qs[i][c4]);
+    if (out.f32) *reinterpret_cast<float4*>(out.f32 + row * out.ld + c4) = y;
+    if (out.pl && planes > 0) {
+      uint32_t h0, l0, h1, l1;
+      split2_op(y.x, y.y, planes, h0, l0);
+      split2_op(y.z, y.w, planes, h1, l1);
+      *reinterpret_cast<uint2*>(out.pl + row * out.ld + c4) = make_uint2(h0, h1);
+      if (planes > 1) *reinterpret_cast<uint2*>(out.pl + (static_cast<long>(out.rows_alloc) + row) * out.ld + c4) = make_uint2(l0, l1);
+    }
+    // the layer input itself, kept for the U-Net skip connections (third K source of the mirrored layer's in-projection)
+    if (keep_x) {
+      const float4 x = *reinterpret_cast<const float4*>(&Ks[i][c4]);
+      if (xcopy.f32) *reinterpret_cast<float4*>(xcopy.f32 + row * xcopy.ld + c4) = x;
+      if (xcopy.pl && planes > 0) {
+        uint32_t h0, l0, h1, l1;
+        split2_op(x.x, x.y, planes, h0, l0);
+        split2_op(x.z, x.w, planes, h1, l1);
+        *reinterpret_cast<uint2*>(xcopy.pl + row * xcopy.ld + c4) = make_uint2(h0, h1);
+        if (planes > 1) *reinterpret_cast<uint2*>(xcopy.pl + (static_cast<long>(xcopy.rows_alloc) + row) * xcopy.ld + c4) = make_uint2(l0, l1);
+      }
+    }
+  }
+  if (trace && tid == 0) atomicMin(trace + 3, ~ktimer());
+}
+
+// The same block with 128 threads per sequence (two adjacent output columns per thread) and at most 120 registers: a CTA then holds
+// 15 360 registers and ~13 KB of shared memory, so TWO of them fit next to the in-projection CTA that still occupies the SM
+// (33 280 registers, 197 KB) and all 256 sequences of a B = 128 step are resident -- row offsets and per-column vectors loaded --
+// when the in-projection ends, instead of ~100 CTAs being launched behind its tail.  __maxnreg__(120) also keeps the per-SM
+// cap at 4 CTAs = 16 warps, the same as the 2 x 256-thread cap of k_attn_ln (more resident warps measured slower,
+// profiles/r02_attn_ln_occupancy.txt).
+template <int MAXT>
+__global__ void __maxnreg__(120) k_attn_ln2(const float* __restrict__ qkvx, const int* __restrict__ off, int S,
+                                                     const float* __restrict__ textkv, int ld_textkv,
+                                                     const float* __restrict__ timekv, const float* __restrict__ res, int ld_res,
+                                                     const float* __restrict__ bo, const float* __restrict__ g,
+                                                     const float* __restrict__ b, Act out, Act xcopy, int planes,
+                                                     unsigned long long* trace) {
+  if (trace && threadIdx.x == 0) atomicMin(trace, ktimer());
+  constexpr int NK = MAXT + 2;
+  __shared__ __align__(16) float Qs[MAXT][256];
+  __shared__ __align__(16) float Ks[NK][256];
+  __shared__ float Ps[MAXT][4][NK];
+  __shared__ float red[2][4][MAXT];
+  const int tid = threadIdx.x, s = blockIdx.x;
+  const int c = 2 * tid;   // this thread's two output columns
+  const int r0 = s < S ? __ldg(off + s) : 0, m = s < S ? min(__ldg(off + s + 1) - r0, MAXT) : 0;
+  const float2 boc = __ldg(reinterpret_cast<const float2*>(bo + c)), gc = __ldg(reinterpret_cast<const float2*>(g + c)),
+               bc = __ldg(reinterpret_cast<const float2*>(b + c));
+  pdl_prologue();
+  if (trace && tid == 0) atomicMin(trace + 1, ~ktimer());
+  if (s >= S || m <= 0) return;
+  const int warp = tid >> 5, lane = tid & 31;
+  const float* tk = textkv + static_cast<long>(s) * ld_textkv;
+  // ---- all global loads up front (one memory round trip)
+  float2 v[4][NK], xr[MAXT];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    const bool on = j < m || j >= MAXT;
+    const float* base = (j < MAXT) ? qkvx + static_cast<long>(r0 + j) * DQX_LD : (j == MAXT ? tk - 256 : timekv - 256);
+    const float2 kk = on ? *reinterpret_cast<const float2*>(base + 256 + c) : make_float2(0.f, 0.f);
+    *reinterpret_cast<float2*>(&Ks[j][c]) = kk;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) v[h][j] = on ? *reinterpret_cast<const float2*>(base + 512 + h * 256 + c) : make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < MAXT; ++i) {
+    float2 q = make_float2(0.f, 0.f);
+    xr[i] = make_float2(0.f, 0.f);
+    if (i < m) {
+      q = *reinterpret_cast<const float2*>(qkvx + static_cast<long>(r0 + i) * DQX_LD + c);
+      xr[i] = *reinterpret_cast<const float2*>(res + static_cast<long>(r0 + i) * ld_res + c);
+    }
+    *reinterpret_cast<float2*>(&Qs[i][c]) = make_float2(q.x * 0.125f, q.y * 0.125f);
+  }
+  __syncthreads();
+  if (trace && tid == 0) atomicMin(trace + 2, ~ktimer());
+  // ---- scores: element e = (i, h, j), one 64-long dot product each
+  for (int e = tid; e < m * 4 * NK; e += 128) {
     const int j = e % NK, h = (e / NK) & 3, i = e / (4 * NK);
     float sc = -INFINITY;
     if (j < m || j >= MAXT) {
@@ -296,7 +467,7 @@ __global__ void __launch_bounds__(256 * SEQS, SEQS == 1 ? 2 : 1) k_attn_ln(const
     }
     Ps[i][h][j] = sc;
   }
-  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  __syncthreads();
   if (tid < m * 4) {
     const int i = tid >> 2, h = tid & 3;
     float mx = -INFINITY;
@@ -312,48 +483,60 @@ __global__ void __launch_bounds__(256 * SEQS, SEQS == 1 ? 2 : 1) k_attn_ln(const
 #pragma unroll
     for (int j = 0; j < NK; ++j) Ps[i][h][j] = pj[j] * inv;
   }
-  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
-  // ---- out[i, c] = sum_h sum_j P[i][h][j] v'[h][j][c]  + out_proj bias + residual
-  float acc[MAXT];
+  __syncthreads();
+  // ---- out[i, c..c+1] = sum_h sum_j P[i][h][j] v'[h][j] + out_proj bias + residual
+  float2 acc[MAXT];
 #pragma unroll
-  for (int i = 0; i < MAXT; ++i) acc[i] = boc + xr[i];
+  for (int i = 0; i < MAXT; ++i) acc[i] = make_float2(boc.x + xr[i].x, boc.y + xr[i].y);
 #pragma unroll
   for (int h = 0; h < 4; ++h)
 #pragma unroll
     for (int j = 0; j < NK; ++j)
 #pragma unroll
-      for (int i = 0; i < MAXT; ++i) acc[i] = fmaf(Ps[i][h][j], v[h][j], acc[i]);  // rows >= m: P stays 0-initialised garbage-free (v = finite)
-  // ---- LayerNorm over the 256 columns (one per thread)
+      for (int i = 0; i < MAXT; ++i) {
+        const float w = Ps[i][h][j];
+        acc[i].x = fmaf(w, v[h][j].x, acc[i].x);
+        acc[i].y = fmaf(w, v[h][j].y, acc[i].y);
+      }
+  // ---- LayerNorm over the 256 columns (two per thread, 4 warps)
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
-    const float w = warp_sum(i < m ? acc[i] : 0.f);
+    const float w = warp_sum(i < m ? acc[i].x + acc[i].y : 0.f);
     if (lane == 0) red[0][warp][i] = w;
   }
-  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  __syncthreads();
   float mean[MAXT];
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[0][w][i];
+    const float t = (red[0][0][i] + red[0][1][i]) + (red[0][2][i] + red[0][3][i]);
     mean[i] = t * (1.f / 256.f);
-    const float dx = acc[i] - mean[i];
-    const float w = warp_sum(i < m ? dx * dx : 0.f);
+    const float dx = acc[i].x - mean[i], dy = acc[i].y - mean[i];
+    const float w = warp_sum(i < m ? dx * dx + dy * dy : 0.f);
     if (lane == 0) red[1][warp][i] = w;
   }
-  asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < MAXT; ++i) {
     if (i < m) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[1][w][i];
+      const float t = (red[1][0][i] + red[1][1][i]) + (red[1][2][i] + red[1][3][i]);
       const float rstd = 1.0f / sqrtf(t * (1.f / 256.f) + LD_EPS);
-      const long o = static_cast<long>(r0 + i) * 256 + c;
-      act_store(out, planes, r0 + i, c, (acc[i] - mean[i]) * rstd * gc + bc);
+      const long row = r0 + i;
+      const float y0 = (acc[i].x - mean[i]) * rstd * gc.x + bc.x, y1 = (acc[i].y - mean[i]) * rstd * gc.y + bc.y;
+      if (out.f32) *reinterpret_cast<float2*>(out.f32 + row * out.ld + c) = make_float2(y0, y1);
+      if (out.pl && planes > 0) {
+        uint32_t hi, lo;
+        split2_op(y0, y1, planes, hi, lo);
+        *reinterpret_cast<uint32_t*>(out.pl + row * out.ld + c) = hi;
+        if (planes > 1) *reinterpret_cast<uint32_t*>(out.pl + (static_cast<long>(out.rows_alloc) + row) * out.ld + c) = lo;
+      }
       // the layer input itself, kept for the U-Net skip connections (third K source of the mirrored layer's in-projection)
-      if (xcopy.f32 || xcopy.pl) act_store(xcopy, planes, r0 + i, c, xr[i]);
-      (void)o;
+      if (xcopy.f32) *reinterpret_cast<float2*>(xcopy.f32 + row * xcopy.ld + c) = xr[i];
+      if (xcopy.pl && planes > 0) {
+        uint32_t hi, lo;
+        split2_op(xr[i].x, xr[i].y, planes, hi, lo);
+        *reinterpret_cast<uint32_t*>(xcopy.pl + row * xcopy.ld + c) = hi;
+        if (planes > 1) *reinterpret_cast<uint32_t*>(xcopy.pl + (static_cast<long>(xcopy.rows_alloc) + row) * xcopy.ld + c) = lo;
+      }
     }
   }
   if (trace && tid == 0) atomicMin(trace + 3, ~ktimer());

@@ -1099,6 +1099,10 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
     if (S > 148 && S <= 296 && getenv("LADIFF_ATTN_2SEQ")) {   // two sequences per CTA: one wave of <= 148 CTAs
       LAUNCHP((k_attn_ln<5, 2>), (S + 1) / 2, 512, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
+    } else if (getenv("LADIFF_ATTN_LN_128")) {   // opt-in: measured slower (20.87 vs 19.55 ms, profiles/r02_attn_ln_occupancy.txt)
+      // 128 threads per sequence: two CTAs fit next to the in-projection CTA of their SM, so every sequence is resident before it ends
+      LAUNCHP((k_attn_ln2<5>), S, 128, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
+           p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
     } else {
       LAUNCHP((k_attn_ln<5, 1>), S, 256, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);
@@ -1173,7 +1177,9 @@ int enqueue_den_tokens(H* h, DenoisePlan* p, cudaStream_t st, int step) {
     // layer input X_l: the packed latents for l = 0, else the X columns of the folded in-projection; X_1..X_4 (= Y_0..Y_3)
     // are also copied out (planes) for the U-Net skip connections of layers 8..5
     const float* res = l == 0 ? p->xin.act.f32 : p->qkv + DQ_LD;
-    CKS(enqueue_den_layer(h, p, st, l, step, res, l == 0 ? 256 : DQX_LD, (l >= 1 && l <= 4) ? p->skip[l - 1].act : none));
+    Act xc = (l >= 1 && l <= 4) ? p->skip[l - 1].act : none;
+    if (mode != LADIFF_MODE_FP32 && xc.pl) xc.f32 = nullptr;   // tensor-core modes read the skip source as operand planes only
+    CKS(enqueue_den_layer(h, p, st, l, step, res, l == 0 ? 256 : DQX_LD, xc));
     const DenLayerW& w = h->den[l];
     if (l == NL - 1) {  // last layer: Y_8 itself (input of encoder.norm in k_cfg_ddim / k_final_ln_out)
       c = LinCall(); c.A = &p->sbuf; c.W = &w.ffn_out; c.M_max = R; c.M_dev = p->R; c.epi = EPI_RES; c.res = p->x3.act.f32;
