@@ -1095,7 +1095,7 @@ int enqueue_den_layer(H* h, DenoisePlan* p, cudaStream_t st, int l, int step, co
   }
   if (fuse_att) {
     // attention + out-proj + residual + LN run as the prologue of the FFN kernel (one launch per layer after the in-projection)
-  } else if (p->T <= 5) {
+  } else if (p->T <= 5 && !getenv("LADIFF_ATTN_LN_MAXT8")) {   // (the env switch runs the 8-latent instantiation on <= 5 latents: test hook)
     if (S > 148 && S <= 296 && getenv("LADIFF_ATTN_2SEQ")) {   // two sequences per CTA: one wave of <= 148 CTAs
       LAUNCHP((k_attn_ln<5, 2>), (S + 1) / 2, 512, 0, st, p->qkv, p->off, S, p->textkv + l * DC_LD, NL * DC_LD,
            p->timekv + static_cast<size_t>(step) * NL * DC_LD + l * DC_LD, res, ld_res, w.out_bias, w.n1g, w.n1b, p->x1.act, xcopy, pl, tr);

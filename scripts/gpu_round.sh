@@ -28,6 +28,10 @@ print({k: d.get(k) for k in ('value','ms_per_step','latency_ms_per_batch','value
         timeout 300 python scripts/trace_step.py bf16x3 50 $B > gpurun_out/${tag}_trace_B$B.txt 2>&1
         head -14 gpurun_out/${tag}_trace_B$B.txt | tail -9
       done ;;
+    variants)   # opt-in / alternate kernel instantiations, selected by environment switches read when a plan is captured
+      for v in LADIFF_ATTN_LN_MAXT8=1 LADIFF_ATTN_2SEQ=1 LADIFF_ATTN_LN_128=1 LADIFF_ATTN_F32_STAGE=1 LADIFF_NO_FFN_TILE=1 LADIFF_ATT_FUSE=1; do
+        echo "== $v"; env $v timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "sampling_vs_reference or batch32 or decode_vs_reference or encode" 2>&1 | tail -1
+      done ;;
     launches)
       LADIFF_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv \
         python bench.py --steps 1 --warmup 1 --quick --no-pipeline > gpurun_out/${tag}_ncu.log 2>&1
