@@ -72,20 +72,20 @@ __global__ void k_text_relu(const float* __restrict__ src, int Btot, int b0, int
   act_store(out, planes, r, c, fmaxf(src[sr * 768 + c], 0.f));
 }
 
-// LayerNorm over 256 columns, one warp per row.  rows = min(rows_max, *rows_dev).
+// LayerNorm over 256 columns, one warp per row (lane = 8 consecutive columns: two 16-byte loads, 16- / 8-byte stores; `in` rows must
+// be 16-byte aligned: ld_in % 4 == 0).  rows = min(rows_max, *rows_dev).
 __global__ void k_layernorm256(const float* __restrict__ in, int ld_in, int rows_max, const int* __restrict__ rows_dev,
                                const float* __restrict__ g, const float* __restrict__ b, Act out, int planes) {
   pdl_prologue();
   const int rows = rows_dev ? min(rows_max, *rows_dev) : rows_max;
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, c0 = lane * 8;
   if (row >= rows) return;
-  float v[8], s = 0.f;
+  const float4 x0 = *reinterpret_cast<const float4*>(in + row * ld_in + c0), x1 = *reinterpret_cast<const float4*>(in + row * ld_in + c0 + 4);
+  float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    v[j] = in[row * ld_in + lane + 32 * j];
-    s += v[j];
-  }
+  for (int j = 0; j < 8; ++j) s += v[j];
   const float mean = warp_sum(s) * (1.f / 256.f);
   float q = 0.f;
 #pragma unroll
@@ -94,10 +94,23 @@ __global__ void k_layernorm256(const float* __restrict__ in, int ld_in, int rows
     q += d * d;
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.f / 256.f) + LD_EPS);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(g + c0 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(b + c0 + 4));
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float y[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = lane + 32 * j;
-    act_store(out, planes, row, c, (v[j] - mean) * rstd * g[c] + b[c]);
+  for (int j = 0; j < 8; ++j) y[j] = (v[j] - mean) * rstd * gg[j] + bb[j];
+  const long o = row * out.ld + c0;
+  if (out.f32) {
+    *reinterpret_cast<float4*>(out.f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(out.f32 + o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+  if (out.pl && planes > 0) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split2_op(y[2 * k], y[2 * k + 1], planes, hi[k], lo[k]);
+    *reinterpret_cast<uint4*>(out.pl + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (planes > 1) *reinterpret_cast<uint4*>(out.pl + static_cast<long>(out.rows_alloc) * out.ld + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -767,11 +780,26 @@ __global__ void k_enc_out(const float* __restrict__ tok, const int* __restrict__
 __global__ void k_dec_init(const float* __restrict__ pe, const int* __restrict__ row_t, const int* __restrict__ R_dev,
                            Act x, int planes) {
   pdl_prologue();
-  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long row = i >> 8;
-  const int c = i & 255;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one thread per 8 columns
+  const long row = i >> 5;
+  const int c0 = (i & 31) * 8;
   if (row >= *R_dev) return;
-  act_store(x, planes, row, c, pe[row_t[row] * 256 + c]);
+  const float* src = pe + static_cast<long>(row_t[row]) * 256 + c0;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+  const long o = row * x.ld + c0;
+  if (x.f32) {
+    *reinterpret_cast<float4*>(x.f32 + o) = a;
+    *reinterpret_cast<float4*>(x.f32 + o + 4) = b;
+  }
+  if (x.pl && planes > 0) {
+    uint32_t hi[4], lo[4];
+    split2_op(a.x, a.y, planes, hi[0], lo[0]);
+    split2_op(a.z, a.w, planes, hi[1], lo[1]);
+    split2_op(b.x, b.y, planes, hi[2], lo[2]);
+    split2_op(b.z, b.w, planes, hi[3], lo[3]);
+    *reinterpret_cast<uint4*>(x.pl + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (planes > 1) *reinterpret_cast<uint4*>(x.pl + static_cast<long>(x.rows_alloc) * x.ld + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
 // zrows[moff[b] + t, :] = z[t, b, :] for t < m[b]  (valid memory rows only)
@@ -869,7 +897,7 @@ __global__ void __launch_bounds__(256, 2) k_cross_ln(const float* __restrict__ x
       float den = 0.f;
 #pragma unroll
       for (int j = 0; j < MAXT; ++j) {
-        sc[f][j] = (j < m) ? expf(sc[f][j] - mx) : 0.f;
+        sc[f][j] = (j < m) ? __expf(sc[f][j] - mx) : 0.f;
         den += sc[f][j];
       }
       const float inv = 1.0f / den;

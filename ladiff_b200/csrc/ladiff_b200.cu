@@ -1438,7 +1438,7 @@ int enqueue_decode_body(H* h, DecodePlan* p, cudaStream_t st) {
   LinCall c;
   c.A = &p->zrows; c.W = &h->memx_all; c.M_max = p->Mmax; c.M_dev = p->Rm; c.out = f32_only(p->memx, NL * CX_LD);
   CKS(launch_linear(h, st, mode, c));
-  LAUNCHP(k_dec_init, cdiv(static_cast<long>(p->Rmax) * 256, 256), 256, 0, st, h->dec_pe, p->frow_t, p->Rf, p->x0.act, pl);
+  LAUNCHP(k_dec_init, cdiv(static_cast<long>(p->Rmax) * 32, 256), 256, 0, st, h->dec_pe, p->frow_t, p->Rf, p->x0.act, pl);
   const ActBuf* x = &p->x0;
   for (int i = 0; i < 4; ++i) {
     CKS(enqueue_dec_layer(h, p, st, i, *x, p->skip[i]));
