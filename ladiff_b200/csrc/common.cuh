@@ -40,6 +40,15 @@ enum Epi : int {
 
 // Programmatic dependent launch: every kernel of the sampling plans starts with pdl_prologue() -- signal that the next
 // grid may begin its own prologue, then wait until the previous grid's results are visible.
+//
+// INVARIANT for everything a kernel reads BEFORE its griddepcontrol.wait (the row counts *M_dev, the sequence offsets off[],
+// per-column vectors, weights): because every grid signals launch_dependents at entry, pre-wait code can overlap grids several
+// launches back, so such data must be complete before the FIRST kernel of the PDL chain starts.  The plans guarantee it
+// structurally: counts / offsets / row maps are produced by k_scan_counts + k_fill_rows, which are launched with LAUNCH (a full
+// stream dependency, no PDL attribute) ahead of the chain (enqueue_offsets / the plan prologues in ladiff_b200.cu), and every
+// table built per call (time / text k-v, modulation, ca_block delta) is written by kernels that precede the step loop and are
+// followed by at least one full-dependency launch (the first kernel after a cross-stream join uses g_skip_pdl_once).  A new
+// producer of pre-wait data must keep that rule: end the producing section with a non-PDL launch.
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
