@@ -558,7 +558,7 @@ def run_own(args):
             "note": ("algorithmic FLOPs per launch = 1280 rows x 4 x lin(256,1024) (the two feed-forward pairs of one denoiser layer, "
                      "SURVEY.md 8d rows 'sa ReLU-FFN' + 'GELU FFN'); bf16x3 issues 3x these on the tensor pipe; duration = CUDA events "
                      f"around 200 back-to-back launches; peak = bf16 burst of {peaks['source']}; traffic = dram read+write per launch "
-                     "of the ncu --set full capture in profiles/r02b_ncu_full_kernels.txt"),
+                     "of the ncu --set full capture in profiles/r02_ncu_full_kernels.txt"),
             "path": path}
     out.update(extra)
     emit(json.dumps(out))
