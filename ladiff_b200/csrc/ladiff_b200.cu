@@ -1250,12 +1250,14 @@ int pick_chains(int B) {
   // Measured on B200 (profiles/r01b_chains.txt): at B = 128 every link is latency-bound and a chain of 32 prompts takes as
   // long as one of 128, so splitting gains nothing; at B = 1024 four chains of 256 prompts overlap one chain's epilogues /
   // launch gaps with another's mainloops (reverse 107 -> 84 ms).
-  // Round 2 (same-box sweep, profiles/r02_large_batch.txt): above 177 prompts one chain no longer fits the co-resident cluster
+  // Round 2 (same-box sweeps, profiles/r02_large_batch.txt): above 177 prompts one chain no longer fits the co-resident cluster
   // feed-forward kernel (1776 latent rows), and two chains that do (B = 256: 2 x 128) beat one chain on the separate linears
   // (reverse 36.3 -> 31.7 ms in the x3 mode, 26.2 -> 24.3 ms in bf16); B = 384: 45.9 -> 44.9 ms; from B = 512 on, chains of
   // 256 stay best (B = 512: 54.6 ms with 2 chains against 57.3 / 59.2 with 3 / 4; B = 768: 78.0 with 3; B = 1024: 110 with 4).
+  // Between 129 and 177 prompts one chain still fits the cluster kernel but no longer one wave of the in-projection / attention
+  // grids: B = 136 / 144: 20.9 / 21.9 ms with one chain against 22.9 / 24.1 with two; B = 160 / 177: 31.6 / 32.0 against 25.3 / 26.1.
   int n = B / 256;
-  if (n < 2 && B > 177) n = 2;
+  if (n < 2 && B >= 150) n = 2;
   return n < 1 ? 1 : (n > 4 ? 4 : n);
 }
 
