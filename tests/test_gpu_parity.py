@@ -214,6 +214,34 @@ def test_sample_stream_matches_sequential(oracle_sd):
         assert a.shape == b.shape and torch.equal(a, b)
 
 
+def test_sample_stream_pairs_batches(oracle_sd):
+    """Batches that fit are sampled two per reverse-loop launch (two chains in one graph): still bit-identical, batch by batch, to
+    the one-batch-at-a-time path -- ragged lengths, batches that cannot be paired (unequal sizes) in between, and pair=False."""
+    import ladiff_b200 as L
+    from ladiff_b200.data import SyntheticDataModule
+    from ladiff_b200.modeltype import LADIFF
+    torch.set_grad_enabled(False)
+    model = LADIFF(L.default_config("humanml3d", num_inference_timesteps=4), SyntheticDataModule(263, 22))
+    model.denoiser.load_state_dict(O.sub(oracle_sd, "denoiser."), strict=True)
+    model.vae.load_state_dict(O.sub(oracle_sd, "vae."), strict=True)
+    model = model.to("cuda:0").eval()
+    g = torch.Generator().manual_seed(78)
+    batches = []
+    for B, hi in ((80, 196), (80, 120), (96, 196), (70, 196), (90, 64), (90, 196), (90, 100)):   # pairs: (80, 80) and the last two 90s
+        lengths = [int(x) for x in torch.randint(20, hi + 1, (B,), generator=g)]
+        lengths[0] = hi
+        batches.append((torch.randn((2 * B, 1, 768), generator=g).cuda(), lengths, torch.randn((B, 5, 256), generator=g).cuda()))
+    assert model._pairable(batches[0], batches[1]) and not model._pairable(batches[2], batches[3]) and model._pairable(batches[5], batches[6])
+    seq = [model.sample_features(t, l, latents=n).clone() for t, l, n in batches]
+    torch.cuda.synchronize()
+    for pair in (True, False):
+        out = [f.clone() for f in model.sample_stream(iter(batches), pair=pair)]
+        torch.cuda.synchronize()
+        assert len(out) == len(seq)
+        for a, b in zip(seq, out):
+            assert a.shape == b.shape and torch.equal(a, b), f"pair={pair}"
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # round 2: the stated configurations themselves against the oracle (VERDICT r1 "parity partial")
 def _bf16_report(name, err):
