@@ -868,50 +868,72 @@ __global__ void __launch_bounds__(256, 2) k_cross_ln(const float* __restrict__ x
     y[f][0] = xv[f][0] + bo4[0].x; y[f][1] = xv[f][1] + bo4[0].y; y[f][2] = xv[f][2] + bo4[0].z; y[f][3] = xv[f][3] + bo4[0].w;
     y[f][4] = xv[f][4] + bo4[1].x; y[f][5] = xv[f][5] + bo4[1].y; y[f][6] = xv[f][6] + bo4[1].z; y[f][7] = xv[f][7] + bo4[1].w;
   }
+  // The 4 frames x MAXT keys partial dot products of a head are reduced over the 32 lanes with a MULTI-VALUE butterfly instead of
+  // one 5-step butterfly per value: the xor-16 and xor-8 steps halve the number of values a lane carries (lanes with bits (4, 3)
+  // = f keep frame f), only the last three steps run on all MAXT values -- 2 MAXT + MAXT + 3 MAXT = 6 MAXT shuffles instead of
+  // 20 MAXT.  Every lane then owns the complete scores of ONE frame, does that frame's softmax once (not all four), and the
+  // probabilities come back to all lanes with one indexed shuffle each.
+  static_assert(F == 4, "the butterfly below is written for four frames per warp");
+  const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
 #pragma unroll 1
   for (int h = 0; h < 4; ++h) {
-    float sc[F][MAXT];
+    float pp[F][MAXT];
 #pragma unroll
     for (int j = 0; j < MAXT; ++j) {
       if (j < m) {                                       // warp-uniform
         const float* row = cx_tab + j * CX_LD + h * 256 + c0;
         const float4 a = *reinterpret_cast<const float4*>(row), c = *reinterpret_cast<const float4*>(row + 4);
-        const float cq = cx_tab[j * CX_LD + 2048 + h];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           float p = xv[f][0] * a.x;
           p = fmaf(xv[f][1], a.y, p); p = fmaf(xv[f][2], a.z, p); p = fmaf(xv[f][3], a.w, p);
           p = fmaf(xv[f][4], c.x, p); p = fmaf(xv[f][5], c.y, p); p = fmaf(xv[f][6], c.z, p); p = fmaf(xv[f][7], c.w, p);
-          sc[f][j] = (warp_sum(p) + cq) * 0.125f;
+          pp[f][j] = p;
         }
       } else {
 #pragma unroll
-        for (int f = 0; f < F; ++f) sc[f][j] = -INFINITY;
+        for (int f = 0; f < F; ++f) pp[f][j] = 0.f;
       }
     }
+    float r2[MAXT];
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-      float mx = sc[f][0];
-#pragma unroll
-      for (int j = 1; j < MAXT; ++j) mx = fmaxf(mx, sc[f][j]);
-      float den = 0.f;
-#pragma unroll
-      for (int j = 0; j < MAXT; ++j) {
-        sc[f][j] = (j < m) ? __expf(sc[f][j] - mx) : 0.f;
-        den += sc[f][j];
-      }
-      const float inv = 1.0f / den;
-#pragma unroll
-      for (int j = 0; j < MAXT; ++j) sc[f][j] *= inv;
+    for (int j = 0; j < MAXT; ++j) {
+      // xor 16: frames {0, 1} stay in the lower half-warp, {2, 3} in the upper one
+      const float k0 = up16 ? pp[2][j] : pp[0][j], s0 = up16 ? pp[0][j] : pp[2][j];
+      const float k1 = up16 ? pp[3][j] : pp[1][j], s1 = up16 ? pp[1][j] : pp[3][j];
+      const float q0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+      const float q1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+      // xor 8: the even frame of the pair stays where bit 3 is clear
+      const float k2 = up8 ? q1 : q0, s2 = up8 ? q0 : q1;
+      r2[j] = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
     }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j) r2[j] += __shfl_xor_sync(0xffffffffu, r2[j], o);
+    // this lane: scores of frame (lane >> 3) & 3 against the m keys -> softmax
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      r2[j] = (j < m) ? (r2[j] + cx_tab[j * CX_LD + 2048 + h]) * 0.125f : -INFINITY;
+      mx = fmaxf(mx, r2[j]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      r2[j] = (j < m) ? __expf(r2[j] - mx) : 0.f;
+      den += r2[j];
+    }
+    const float inv = 1.0f / den;
 #pragma unroll
     for (int j = 0; j < MAXT; ++j) {
       if (j < m) {
+        const float pj = r2[j] * inv;
         const float* row = cx_tab + j * CX_LD + 1024 + h * 256 + c0;
         const float4 a = *reinterpret_cast<const float4*>(row), c = *reinterpret_cast<const float4*>(row + 4);
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          const float p = sc[f][j];
+          const float p = __shfl_sync(0xffffffffu, pj, f * 8);   // lane 8 f holds frame f
           y[f][0] = fmaf(p, a.x, y[f][0]); y[f][1] = fmaf(p, a.y, y[f][1]); y[f][2] = fmaf(p, a.z, y[f][2]); y[f][3] = fmaf(p, a.w, y[f][3]);
           y[f][4] = fmaf(p, c.x, y[f][4]); y[f][5] = fmaf(p, c.y, y[f][5]); y[f][6] = fmaf(p, c.z, y[f][6]); y[f][7] = fmaf(p, c.w, y[f][7]);
         }
