@@ -207,3 +207,28 @@ def test_bench_algorithmic_flops_match_survey():
     assert sum(lengths) == 16092                                   # seeded ragged batch
     d, c = bench.algorithmic_flops(lengths)
     assert abs((d + c) / 1e12 - 1.376) < 0.002 and abs(c / 1e12 - 0.307) < 0.002
+
+
+def test_sample_stream_pairing_rules():
+    """Host logic of LADIFF.sample_stream's batch pairing (no GPU): which consecutive batches may share one reverse-loop call,
+    and how their classifier-free-guidance halves are merged ([uncond | cond] per batch -> [uncond a, uncond b | cond a, cond b])."""
+    from ladiff_b200.modeltype import LADIFF
+    pairable = LADIFF._pairable.__get__(LADIFF.__new__(LADIFF))      # uses class constants only
+
+    def item(n, cfg=True, lat=True, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        t = torch.randn(((2 if cfg else 1) * n, 1, 768), generator=g)
+        return t, [196] * n, (torch.randn((n, 5, 256), generator=g) if lat else None)
+
+    assert pairable(item(128), item(128)) and pairable(item(80), item(80)) and pairable(item(177), item(177))
+    assert not pairable(item(64), item(64))            # 128 prompts in one call: one chain -- nothing to gain
+    assert not pairable(item(128), item(96))           # unequal batches would not map one batch to one chain
+    assert not pairable(item(178), item(178))          # a chain of more than 177 prompts leaves the cluster feed-forward kernel
+    assert not pairable(item(128), item(128, lat=False)) and not pairable(item(128), item(128, cfg=False))
+    a, b = item(3, seed=1), item(3, seed=2)
+    text, lengths, lat = LADIFF._merge_pair(a, b)
+    assert lengths == a[1] + b[1] and torch.equal(lat, torch.cat([a[2], b[2]]))
+    assert torch.equal(text[:3], a[0][:3]) and torch.equal(text[3:6], b[0][:3])            # unconditional halves first
+    assert torch.equal(text[6:9], a[0][3:]) and torch.equal(text[9:], b[0][3:])
+    text, _, lat = LADIFF._merge_pair(item(2, cfg=False, lat=False), item(2, cfg=False, lat=False, seed=5))
+    assert text.shape[0] == 4 and lat is None
