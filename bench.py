@@ -403,8 +403,12 @@ def run_own(args):
         t2, l2, z2 = model._merge_pair((text_d, lengths, noise_d), (text_d, lengths, noise_d))
         zz = model._diffusion_reverse(t2, l2, latents=z2)
         n1 = eng.last_launch_count
-        model.vae.decode(zz[:, :B].contiguous(), lengths)      # (sample_stream decodes the two batches of a pair separately)
-        launches = n1 / 2.0 + eng.last_launch_count
+        if B * max(lengths) > model.DECODE_MERGE_MIN_ROWS:        # sample_stream then decodes the pair in one call
+            model.vae.decode(zz, l2)
+            launches = (n1 + eng.last_launch_count) / 2.0
+        else:
+            model.vae.decode(zz[:, :B].contiguous(), lengths)
+            launches = n1 / 2.0 + eng.last_launch_count
         del zz, t2, z2
         torch.cuda.synchronize()
     ms_total = timed_pipe(args.steps, W, False) if pipelined else ms_seq
@@ -551,7 +555,7 @@ def run_own(args):
         "run": {"mode": args.mode, "l2": "L2 flushed (256 MiB write) between timed iterations",
                 "collective": "all_gather_into_tensor of motions per step" if world > 1 else "none",
                 "schedule": ("pipelined over the K steps (LADIFF.sample_stream: two consecutive batches of 128 share one reverse-loop launch "
-                             "as two independent chains of one CUDA graph, and the decode of a pair runs on a low-priority stream under the "
+                             "as two independent chains of one CUDA graph, the pair is decoded in one call on a low-priority stream under the "
                              "reverse loop of the next pair; results bit-identical to one batch at a time -- latency_ms_per_batch / p50 are "
                              "the one-batch-at-a-time figures)") if pipelined else "one batch at a time"},
         "latency_ms_per_batch": ms_seq / args.steps,

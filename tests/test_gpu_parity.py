@@ -227,11 +227,14 @@ def test_sample_stream_pairs_batches(oracle_sd):
     model = model.to("cuda:0").eval()
     g = torch.Generator().manual_seed(78)
     batches = []
-    for B, hi in ((80, 196), (80, 120), (96, 196), (70, 196), (90, 64), (90, 196), (90, 100)):   # pairs: (80, 80) and the last two 90s
+    # pairs: (80, 80) [80 x 120 frames < 75 row tiles: two decodes], the two 90s [one of them small: two decodes], and the two
+    # 100s [both past 74 row tiles, different max lengths: ONE merged decode, sliced]
+    for B, hi in ((80, 196), (80, 120), (96, 196), (70, 196), (90, 64), (90, 196), (90, 100), (100, 196), (100, 150)):
         lengths = [int(x) for x in torch.randint(20, hi + 1, (B,), generator=g)]
         lengths[0] = hi
         batches.append((torch.randn((2 * B, 1, 768), generator=g).cuda(), lengths, torch.randn((B, 5, 256), generator=g).cuda()))
     assert model._pairable(batches[0], batches[1]) and not model._pairable(batches[2], batches[3]) and model._pairable(batches[5], batches[6])
+    assert model._pairable(batches[7], batches[8]) and all(len(l) * max(l) > model.DECODE_MERGE_MIN_ROWS for _, l, _ in batches[7:9])
     seq = [model.sample_features(t, l, latents=n).clone() for t, l, n in batches]
     torch.cuda.synchronize()
     for pair in (True, False):
