@@ -356,20 +356,27 @@ def run_own(args):
     d2h = torch.cuda.Stream(device=dev)      # result read-back on its own stream: the next batch's H2D copies (caller's stream,
                                              # which sample_stream orders the reverse loop after) must not queue behind it
 
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None   # same reason for the all-gather: off the caller's stream
+
     def run_pipe(n, host):
         cur = torch.cuda.current_stream()
         for feats in model.sample_stream(batches(n, host)):
             if world > 1:
-                # the only collective: motions over NVLink, straight into the preallocated [world * B, 196, 263] buffer; it is
-                # enqueued on the caller's stream while the NEXT batch's reverse loop already runs on the high-priority stream
-                dist.all_gather_into_tensor(gather, feats)
+                # the only collective: motions over NVLink, straight into the preallocated [world * B, 196, 263] buffer, on its
+                # own stream, while the NEXT pair's reverse loop already runs on the high-priority stream
+                comm.wait_stream(cur)
+                with torch.cuda.stream(comm):
+                    dist.all_gather_into_tensor(gather, feats)
+                feats.record_stream(comm)
             if host:
                 d2h.wait_stream(cur)
                 with torch.cuda.stream(d2h):
                     out_h.copy_(feats, non_blocking=True)
                 feats.record_stream(d2h)
+        if world > 1:
+            cur.wait_stream(comm)                # the timed region ends after the last all-gather ...
         if host:
-            cur.wait_stream(d2h)                 # the timed region ends after the last read-back
+            cur.wait_stream(d2h)                 # ... and the last read-back
 
     def timed_pipe(K, W, host):
         run_pipe(W, host)
